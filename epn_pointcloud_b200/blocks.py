@@ -1,0 +1,212 @@
+"""Block wrappers around the fused convs -- mirror of SPConvNets/utils/base_so3conv.py:16-215
+(`preprocess_input`, `InterSO3ConvBlock`, `IntraSO3ConvBlock`, `SeparableSO3ConvBlock`,
+`BasicSO3ConvBlock`) with identical constructor arguments and sub-module names, so a
+reference `state_dict` loads key for key, plus the backbone parameter arithmetic of the three
+shipped models (SPConvNets/models/cls_so3net_pn.py:41-150, reg_so3net.py:76-171,
+inv_so3net_pn.py:66-163).
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as L
+from . import modules as sptk
+
+
+def preprocess_input(x, na, add_center=True):
+    """[nb, np, 3] -> SphericalPointCloud(xyz [nb,3,np], occupancy feats [nb,1,np,na])
+    (base_so3conv.py:16-23)."""
+    if x.shape[2] != 3:
+        raise NotImplementedError("normals input: broken upstream (so3conv/functional.py:35-36)")
+    if add_center:
+        center = x.mean(1, keepdim=True)
+        x = torch.cat((center, x), dim=1)[:, :-1]
+    xyz = x[:, :, :3].permute(0, 2, 1).contiguous()
+    if add_center:  # feature of the dummy centre point is zeroed: needs the real tensor
+        return sptk.SphericalPointCloud(xyz, L.get_occupancy_features(x, na, True), None)
+    return sptk.SphericalPointCloud(xyz, None, None, occupancy=(x.shape[0], x.shape[1], na))
+
+
+class IntraSO3ConvBlock(nn.Module):
+    """base_so3conv.py:32-62"""
+
+    def __init__(self, dim_in, dim_out, norm=None, activation="relu", dropout_rate=0):
+        super().__init__()
+        if norm is not None:
+            norm = getattr(nn, norm)
+        self.conv = sptk.IntraSO3Conv(dim_in, dim_out)
+        self.norm = nn.InstanceNorm2d(dim_out, affine=False) if norm is None else norm(dim_out)
+        self.relu = None if activation is None else getattr(F, activation)
+        self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
+
+    def forward(self, x):
+        x = self.conv(x)
+        feat = self.norm(x.feats)
+        if self.relu is not None:
+            feat = self.relu(feat)
+        if self.training and self.dropout is not None:
+            feat = self.dropout(feat)
+        return sptk.SphericalPointCloud(x.xyz, feat, x.anchors)
+
+
+class InterSO3ConvBlock(nn.Module):
+    """base_so3conv.py:88-126"""
+
+    def __init__(self, dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor, multiplier, kanchor=60,
+                 lazy_sample=None, norm=None, activation="relu", pooling="none", dropout_rate=0):
+        super().__init__()
+        if lazy_sample is None:
+            lazy_sample = True
+        if norm is not None:
+            norm = getattr(nn, norm)
+        pooling_method = None if pooling == "none" else pooling
+        self.conv = sptk.InterSO3Conv(dim_in, dim_out, kernel_size, stride, radius, sigma, n_neighbor,
+                                      kanchor=kanchor, lazy_sample=lazy_sample, pooling=pooling_method)
+        self.norm = nn.InstanceNorm2d(dim_out, affine=False) if norm is None else norm(dim_out)
+        self.relu = None if activation is None else getattr(F, activation)
+        self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
+
+    def forward(self, x, inter_idx=None, inter_w=None):
+        inter_idx, inter_w, sample_idx, x = self.conv(x, inter_idx, inter_w)
+        feat = self.norm(x.feats)
+        if self.relu is not None:
+            feat = self.relu(feat)
+        if self.training and self.dropout is not None:
+            feat = self.dropout(feat)
+        return inter_idx, inter_w, sample_idx, sptk.SphericalPointCloud(x.xyz, feat, x.anchors)
+
+
+class SeparableSO3ConvBlock(nn.Module):
+    """inter conv -> intra conv, plus the 1x1-conv skip branch (base_so3conv.py:168-215)"""
+
+    def __init__(self, params):
+        super().__init__()
+        dim_in = params["dim_in"]
+        dim_out = params["dim_out"]
+        norm = getattr(nn, params["norm"]) if "norm" in params.keys() else None
+        self.use_intra = params["kanchor"] > 1
+        self.inter_conv = InterSO3ConvBlock(**params)
+        intra_args = {"dim_in": dim_out, "dim_out": dim_out, "dropout_rate": params["dropout_rate"],
+                      "activation": params["activation"]}
+        if self.use_intra:
+            self.intra_conv = IntraSO3ConvBlock(**intra_args)
+        self.stride = params["stride"]
+        self.skip_conv = nn.Conv2d(dim_in, dim_out, 1)
+        self.norm = nn.InstanceNorm2d(dim_out, affine=False) if norm is None else norm(dim_out)
+        self.relu = getattr(F, params["activation"])
+
+    def forward(self, x, inter_idx, inter_w):
+        skip_feature = x.feats
+        inter_idx, inter_w, sample_idx, x = self.inter_conv(x, inter_idx, inter_w)
+        if self.use_intra:
+            x = self.intra_conv(x)
+        if self.stride > 1:
+            skip_feature = L.batched_index_select(skip_feature, 2, sample_idx.long())
+        skip_feature = self.skip_conv(skip_feature)
+        skip_feature = self.relu(self.norm(skip_feature))
+        x_out = sptk.SphericalPointCloud(x.xyz, x.feats + skip_feature, x.anchors)
+        return inter_idx, inter_w, sample_idx, x_out
+
+    def get_anchor(self):
+        return torch.from_numpy(L.get_anchors())
+
+
+class BasicSO3ConvBlock(nn.Module):
+    """A list of conv blocks (base_so3conv.py:129-166)"""
+
+    def __init__(self, params):
+        super().__init__()
+        self.blocks = nn.ModuleList()
+        self.layer_types = []
+        for param in params:
+            if param["type"] == "intra_block":
+                conv = IntraSO3ConvBlock(**param["args"])
+            elif param["type"] == "inter_block":
+                conv = InterSO3ConvBlock(**param["args"])
+            elif param["type"] == "separable_block":
+                conv = SeparableSO3ConvBlock(param["args"])
+            else:
+                raise ValueError("No such type of SO3Conv %s" % param["type"])
+            self.layer_types.append(param["type"])
+            self.blocks.append(conv)
+        self.params = params
+
+    def forward(self, x):
+        inter_idx, inter_w = None, None
+        for conv, param in zip(self.blocks, self.params):
+            if param["type"] in ["inter", "inter_block", "separable_block"]:
+                inter_idx, inter_w, _, x = conv(x, inter_idx, inter_w)
+                if param["args"]["stride"] > 1:
+                    inter_idx, inter_w = None, None
+            elif param["type"] in ["intra_block"]:
+                x = conv(x)
+            else:
+                raise ValueError("No such type of SO3Conv %s" % param["type"])
+        return x
+
+    def get_anchor(self):
+        return torch.from_numpy(L.get_anchors())
+
+
+# --------------------------------------------------------- backbone arithmetic
+def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
+                        mlps=((64, 64), (128, 128), (256, 256), (256,)), strides=(2, 2, 2, 2),
+                        initial_radius_ratio=0.2, sampling_ratio=0.4, sampling_density=0.5,
+                        kernel_multiplier=2, input_radius=1.0, sigma_ratio=0.5, xyz_pooling=None):
+    """Layer hyper-parameters of the ModelNet40 classification backbone
+    (cls_so3net_pn.py:41-150): per-layer radius / sigma / neighbour count / stride."""
+    strides = list(strides)
+    na = kanchor
+    if input_num > 1024:
+        sampling_ratio /= (input_num / 1024)
+        strides[0] = int(2 * (input_num / 1024))
+    n_layer = len(mlps)
+    stride_multipliers = [2 ** i for i in range(n_layer + 1)]
+    num_centers = [int(input_num / m) for m in stride_multipliers]
+    radius_ratio = [initial_radius_ratio * m ** sampling_density for m in stride_multipliers]
+    radii = [r * input_radius for r in radius_ratio]
+    weighted_sigma = [sigma_ratio * radii[0] ** 2]
+    for i in range(len(strides)):
+        weighted_sigma.append(weighted_sigma[i] * 2)
+    backbone = []
+    dim_in = 1
+    for i, block in enumerate(mlps):
+        block_param = []
+        for j, dim_out in enumerate(block):
+            lazy_sample = i != 0 or j != 0
+            stride_conv = i == 0 or xyz_pooling != "stride"
+            neighbor = int(sampling_ratio * num_centers[i] * radius_ratio[i] ** (1 / sampling_density))
+            if j == 0:
+                inter_stride = strides[i]
+                nidx = i if i == 0 else i + 1
+                if stride_conv:
+                    neighbor *= 2
+            else:
+                inter_stride = 1
+                nidx = i + 1
+            block_param.append({
+                "type": "inter_block" if na < 60 else "separable_block",
+                "args": {"dim_in": dim_in, "dim_out": dim_out, "kernel_size": 1, "stride": inter_stride,
+                         "radius": radii[nidx], "sigma": weighted_sigma[nidx], "n_neighbor": neighbor,
+                         "lazy_sample": lazy_sample, "dropout_rate": dropout_rate, "multiplier": kernel_multiplier,
+                         "activation": "leaky_relu", "pooling": xyz_pooling, "kanchor": na, "norm": "BatchNorm2d"},
+            })
+            dim_in = dim_out
+        backbone.append(block_param)
+    return backbone
+
+
+class SO3ConvBackbone(nn.Module):
+    """preprocess_input + the list of BasicSO3ConvBlocks, i.e. ClsSO3ConvModel.forward minus the
+    classification head (cls_so3net_pn.py:16-36)."""
+
+    def __init__(self, backbone_params, na):
+        super().__init__()
+        self.backbone = nn.ModuleList([BasicSO3ConvBlock(bp) for bp in backbone_params])
+        self.na_in = na
+
+    def forward(self, x):
+        x = preprocess_input(x, self.na_in, False)
+        for block in self.backbone:
+            x = block(x)
+        return x

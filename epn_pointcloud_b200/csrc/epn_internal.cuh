@@ -1,0 +1,42 @@
+// Internal launch interfaces shared between the translation units of libepn_b200.so.
+#pragma once
+#include "epn_common.cuh"
+
+namespace epn {
+
+struct InterGeom {
+    const float *xyz;      // [B,3,P_in]
+    const float *centers;  // [B,3,P]
+    const float *anchors;  // [na,3,3]
+    const float *kernels;  // [ks,3]
+    float sigma;
+};
+
+// Matrix operand of the generic GEMM: element (row, col) of slice z lives at
+// ptr + z*stride_z + row*stride_row + col*stride_col.  For A rows are m and
+// cols are k; for B rows are k and cols are n.
+struct GemmOperand {
+    const float *ptr;
+    long long stride_z, stride_row, stride_col;
+};
+
+// epn_group.cu -- grouped slabs are addressed as
+//   slab[b*stride_b + (c*ks+k)*stride_ck + (p - p_off)*na + a],  p in [p_off, p_off+p_cnt)
+int launch_inter_group_fwd(const float *feats, const int32_t *idx, const float *inter_w, const InterGeom &g,
+                           float *out, long long stride_b, long long stride_ck, int p_off, int p_cnt, int b,
+                           int c, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
+int launch_inter_group_bwd(const float *dgrouped, long long stride_b, long long stride_ck, int p_off, int p_cnt,
+                           const int32_t *idx, const float *inter_w, const InterGeom &g, float *dfeats, int b,
+                           int c, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
+int launch_intra_group_fwd(const float *feats, const int32_t *intra_idx, float *out, long long stride_b,
+                           long long stride_ck, int p_off, int p_cnt, int b, int c, int p, int na, int kn,
+                           cudaStream_t s);
+int launch_intra_group_bwd(const float *dgrouped, long long stride_b, long long stride_ck, int p_off, int p_cnt,
+                           const int32_t *intra_idx, float *dfeats, int b, int c, int p, int na, int kn,
+                           cudaStream_t s);
+
+// epn_gemm_simt.cu
+int launch_sgemm(const GemmOperand &A, const GemmOperand &B, float *C, long long c_stride_z, long long ldc,
+                 int M, int N, int K, int batch, int split_k, int accumulate, cudaStream_t s);
+
+}  // namespace epn

@@ -1,0 +1,356 @@
+"""Tensor-level bindings of the C ABI (boundary #1 of SURVEY.md section 8b).
+
+Every function takes/returns CUDA torch tensors in the reference's layouts, allocates
+the outputs with torch (the library itself never allocates), launches on torch's
+current stream and raises RuntimeError on any failure.  The three namespaces
+`grouping`, `gathering`, `zpconv` at the bottom expose exactly the names, argument
+order and return shapes of the reference's pybind modules `vgtk.cuda.grouping`
+(vgtk/vgtk/cuda/grouping_cuda.cpp:176-181), `vgtk.cuda.gathering`
+(gathering_cuda.cpp:61-65) and `vgtk.cuda.zpconv` (zpconv_cuda.cpp:112-118).
+"""
+import types
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:  # same contract as CHECK_CUDA, grouping_cuda.cpp:66-68
+            raise RuntimeError("epn_pointcloud_b200: tensor must be a CUDA tensor (no CPU fallback exists)")
+        if not t.is_contiguous():
+            raise RuntimeError("epn_pointcloud_b200: tensor must be contiguous")
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _i32(t):
+    return t if t.dtype == torch.int32 else t.int()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    """One grow-only scratch buffer per (device, stream); 256-B aligned by the torch allocator."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ------------------------------------------------------------------ index ops
+def ball_query(new_xyz, xyz, radius, nsample):
+    """new_xyz [b,3,m], xyz [b,3,n] -> idx int32 [b,m,nsample] (grouping_cuda.cpp:71-86)."""
+    new_xyz, xyz = _f32(new_xyz), _f32(xyz)
+    _require_cuda(new_xyz, xyz)
+    b, _, m = new_xyz.shape
+    n = xyz.shape[2]
+    idx = torch.empty(b, m, nsample, dtype=torch.int32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().epn_ball_query_f32(_p(new_xyz), _p(xyz), _p(idx), b, n, m, float(radius),
+                                                 int(nsample), _stream()), "epn_ball_query_f32")
+    return idx
+
+
+def furthest_point_sampling(xyz, m):
+    """xyz [b,3,n] -> idx int32 [b,m] (grouping_cuda.cpp:160-174)."""
+    xyz = _f32(xyz)
+    _require_cuda(xyz)
+    b, _, n = xyz.shape
+    idx = torch.empty(b, m, dtype=torch.int32, device=xyz.device)
+    L = _lib.lib()
+    with torch.cuda.device(xyz.device):
+        wsb = L.epn_fps_workspace_bytes(b, n)
+        ws = _workspace(wsb, xyz.device) if wsb else None
+        _lib.check(L.epn_fps_f32(_p(xyz), _p(ws), _p(idx), b, n, int(m), _stream()), "epn_fps_f32")
+    return idx
+
+
+def gather_points_forward(points, idx):
+    """points [b,c,n], idx int32 [b,m] -> float32 [b,c,m] (gathering_cuda.cpp:29-43)."""
+    points, idx = _f32(points), _i32(idx)
+    _require_cuda(points, idx)
+    b, c, n = points.shape
+    m = idx.shape[1]
+    out = torch.empty(b, c, m, dtype=torch.float32, device=points.device)
+    with torch.cuda.device(points.device):
+        _lib.check(_lib.lib().epn_gather_fwd_f32(_p(points), _p(idx), _p(out), b, c, n, m, _stream()),
+                   "epn_gather_fwd_f32")
+    return out
+
+
+def gather_points_backward(grad_out, idx, npoint):
+    """grad_out [b,c,m], idx [b,m] -> [b,c,npoint] (gathering_cuda.cpp:46-59)."""
+    grad_out, idx = _f32(grad_out), _i32(idx)
+    _require_cuda(grad_out, idx)
+    b, c, m = grad_out.shape
+    out = torch.zeros(b, c, int(npoint), dtype=torch.float32, device=grad_out.device)
+    with torch.cuda.device(grad_out.device):
+        _lib.check(_lib.lib().epn_gather_bwd_f32(_p(grad_out), _p(idx), _p(out), b, c, int(npoint), m, _stream()),
+                   "epn_gather_bwd_f32")
+    return out
+
+
+# ------------------------------------------------------------- zpconv surface
+def inter_zpconv_forward(inter_idx, inter_w, feats):
+    """idx/w [b,np,na,ks,ann], feats [b,c,nq,na] -> [b,c,ks,np,na] (zpconv_cuda.cpp:41-58)."""
+    inter_idx, inter_w, feats = _i32(inter_idx), _f32(inter_w), _f32(feats)
+    _require_cuda(inter_idx, inter_w, feats)
+    b, np_, na, ks, ann = inter_idx.shape
+    c, nq = feats.shape[1], feats.shape[2]
+    out = torch.empty(b, c, ks, np_, na, dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().epn_zp_inter_fwd_f32(_p(inter_idx), _p(inter_w), _p(feats), _p(out), b, c, nq, np_, na,
+                                                   ks, ann, _stream()), "epn_zp_inter_fwd_f32")
+    return out
+
+
+def inter_zpconv_backward(inter_idx, inter_w, grad, npoint):
+    """grad [b,c,ks,np,na] -> [b,c,npoint,na] (zpconv_cuda.cpp:60-77)."""
+    inter_idx, inter_w, grad = _i32(inter_idx), _f32(inter_w), _f32(grad)
+    _require_cuda(inter_idx, inter_w, grad)
+    b, np_, na, ks, ann = inter_idx.shape
+    c = grad.shape[1]
+    out = torch.zeros(b, c, int(npoint), na, dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _lib.check(_lib.lib().epn_zp_inter_bwd_f32(_p(inter_idx), _p(inter_w), _p(grad), _p(out), b, c, int(npoint),
+                                                   np_, na, ks, ann, _stream()), "epn_zp_inter_bwd_f32")
+    return out
+
+
+def intra_zpconv_forward(intra_idx, intra_w, feats):
+    """idx [na_out,ann], w [na_out,ks,ann], feats [b,c,np,na_in] -> [b,c,ks,np,na_out] (zpconv_cuda.cpp:79-95)."""
+    intra_idx, intra_w, feats = _i32(intra_idx), _f32(intra_w), _f32(feats)
+    _require_cuda(intra_idx, intra_w, feats)
+    na_out, ann = intra_idx.shape
+    ks = intra_w.shape[1]
+    b, c, np_, na_in = feats.shape
+    out = torch.empty(b, c, ks, np_, na_out, dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().epn_zp_intra_fwd_f32(_p(intra_idx), _p(intra_w), _p(feats), _p(out), b, c, np_, na_in,
+                                                   na_out, ks, ann, _stream()), "epn_zp_intra_fwd_f32")
+    return out
+
+
+def intra_zpconv_backward(intra_idx, intra_w, grad, anchor_in):
+    """grad [b,c,ks,np,na_out] -> [b,c,np,anchor_in] (zpconv_cuda.cpp:97-110)."""
+    intra_idx, intra_w, grad = _i32(intra_idx), _f32(intra_w), _f32(grad)
+    _require_cuda(intra_idx, intra_w, grad)
+    na_out, ann = intra_idx.shape
+    ks = intra_w.shape[1]
+    b, c, _, np_, _ = grad.shape
+    out = torch.zeros(b, c, np_, int(anchor_in), dtype=torch.float32, device=grad.device)
+    with torch.cuda.device(grad.device):
+        _lib.check(_lib.lib().epn_zp_intra_bwd_f32(_p(intra_idx), _p(intra_w), _p(grad), _p(out), b, c, np_,
+                                                   int(anchor_in), na_out, ks, ann, _stream()), "epn_zp_intra_bwd_f32")
+    return out
+
+
+# ----------------------------------------------------- live-path grouping stages
+def inter_weights(xyz, centers, idx, anchors, kernels, sigma):
+    """-> inter_w [b,p,na,ks,nn] (so3conv/functional.py:180-218)."""
+    _require_cuda(xyz, centers, idx, anchors, kernels)
+    b, _, p_in = xyz.shape
+    p, nn = idx.shape[1], idx.shape[2]
+    na, ks = anchors.shape[0], kernels.shape[0]
+    w = torch.empty(b, p, na, ks, nn, dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        _lib.check(_lib.lib().epn_inter_weights_f32(_p(xyz), _p(centers), _p(idx), _p(anchors), _p(kernels),
+                                                    float(sigma), _p(w), b, p_in, p, nn, na, ks, _stream()),
+                   "epn_inter_weights_f32")
+    return w
+
+
+def inter_group_fwd(feats, idx, inter_w=None, geom=None):
+    """feats [b,c,p_in,na] (or None = occupancy ones, c=1), idx [b,p,nn], and either inter_w
+    [b,p,na,ks,nn] or geom=(xyz, centers, anchors, kernels, sigma) -> [b,c,ks,p,na]."""
+    _require_cuda(feats, idx, inter_w)
+    b, p, nn = idx.shape
+    if inter_w is not None:
+        na, ks = inter_w.shape[2], inter_w.shape[3]
+        xyz = centers = anchors = kernels = None
+        sigma = 1.0
+    else:
+        xyz, centers, anchors, kernels, sigma = geom
+        _require_cuda(xyz, centers, anchors, kernels)
+        na, ks = anchors.shape[0], kernels.shape[0]
+    if feats is not None:
+        c, p_in = feats.shape[1], feats.shape[2]
+    else:
+        c, p_in = 1, xyz.shape[2]
+    out = torch.empty(b, c, ks, p, na, dtype=torch.float32, device=idx.device)
+    with torch.cuda.device(idx.device):
+        _lib.check(_lib.lib().epn_inter_group_fwd_f32(_p(feats), _p(idx), _p(inter_w), _p(xyz), _p(centers),
+                                                      _p(anchors), _p(kernels), float(sigma), _p(out), b, c, p_in, p,
+                                                      nn, na, ks, _stream()), "epn_inter_group_fwd_f32")
+    return out
+
+
+def inter_group_bwd(dout, idx, p_in, inter_w=None, geom=None):
+    """dout [b,c,ks,p,na] -> dfeats [b,c,p_in,na]."""
+    _require_cuda(dout, idx, inter_w)
+    b, c, ks, p, na = dout.shape
+    nn = idx.shape[2]
+    if inter_w is not None:
+        xyz = centers = anchors = kernels = None
+        sigma = 1.0
+    else:
+        xyz, centers, anchors, kernels, sigma = geom
+        _require_cuda(xyz, centers, anchors, kernels)
+    dfeats = torch.zeros(b, c, int(p_in), na, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        _lib.check(_lib.lib().epn_inter_group_bwd_f32(_p(dout), _p(idx), _p(inter_w), _p(xyz), _p(centers),
+                                                      _p(anchors), _p(kernels), float(sigma), _p(dfeats), b, c,
+                                                      int(p_in), p, nn, na, ks, _stream()), "epn_inter_group_bwd_f32")
+    return dfeats
+
+
+def intra_group_fwd(feats, intra_idx):
+    """feats [b,c,p,na], intra_idx int32 [na,kn] -> [b,c,kn,p,na] (so3conv/functional.py:221-268)."""
+    _require_cuda(feats, intra_idx)
+    b, c, p, na = feats.shape
+    kn = intra_idx.shape[1]
+    out = torch.empty(b, c, kn, p, na, dtype=torch.float32, device=feats.device)
+    with torch.cuda.device(feats.device):
+        _lib.check(_lib.lib().epn_intra_group_fwd_f32(_p(feats), _p(intra_idx), _p(out), b, c, p, na, kn, _stream()),
+                   "epn_intra_group_fwd_f32")
+    return out
+
+
+def intra_group_bwd(dout, intra_idx):
+    """dout [b,c,kn,p,na] -> dfeats [b,c,p,na]; columns of intra_idx must be permutations."""
+    _require_cuda(dout, intra_idx)
+    b, c, kn, p, na = dout.shape
+    dfeats = torch.empty(b, c, p, na, dtype=torch.float32, device=dout.device)
+    with torch.cuda.device(dout.device):
+        _lib.check(_lib.lib().epn_intra_group_bwd_f32(_p(dout), _p(intra_idx), _p(dfeats), b, c, p, na, kn, _stream()),
+                   "epn_intra_group_bwd_f32")
+    return dfeats
+
+
+# -------------------------------------------------------------------- fused convs
+def basic_conv_fwd(x, W):
+    """x [b,c,ks,p,na], W [co, c*ks] -> [b,co,p,na] (so3conv/modules.py:48-55)."""
+    _require_cuda(x, W)
+    b, c, ks, p, na = x.shape
+    co = W.shape[0]
+    out = torch.empty(b, co, p, na, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().epn_basic_conv_fwd_f32(_p(x), _p(W), _p(out), b, c * ks, co, p * na, _stream()),
+                   "epn_basic_conv_fwd_f32")
+    return out
+
+
+def basic_conv_bwd(dout, x, W, need_dx=True, need_dw=True):
+    _require_cuda(dout, x, W)
+    b, c, ks, p, na = x.shape
+    co = W.shape[0]
+    dx = torch.empty_like(x) if need_dx else None
+    dW = torch.empty_like(W) if need_dw else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().epn_basic_conv_bwd_f32(_p(dout), _p(x), _p(W), _p(dx), _p(dW), b, c * ks, co, p * na,
+                                                     _stream()), "epn_basic_conv_bwd_f32")
+    return dx, dW
+
+
+def inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W):
+    """Fused InterSO3Conv minus sampling/ball query -> [b,c_out,p,na].  feats None = occupancy ones."""
+    _require_cuda(feats, xyz, centers, idx, anchors, kernels, W)
+    b, _, p_in = xyz.shape
+    p, nn = idx.shape[1], idx.shape[2]
+    na, ks = anchors.shape[0], kernels.shape[0]
+    c_in = 1 if feats is None else feats.shape[1]
+    c_out = W.shape[0]
+    if W.shape[1] != c_in * ks:
+        raise RuntimeError("W must be [c_out, c_in*ks] = [%d, %d], got %s" % (c_out, c_in * ks, tuple(W.shape)))
+    out = torch.empty(b, c_out, p, na, dtype=torch.float32, device=xyz.device)
+    L = _lib.lib()
+    with torch.cuda.device(xyz.device):
+        wsb = L.epn_inter_so3conv_workspace_bytes(b, c_in, c_out, p_in, p, nn, na, ks, 0)
+        ws = _workspace(wsb, xyz.device)
+        _lib.check(L.epn_inter_so3conv_fwd_f32(_p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors), _p(kernels),
+                                               float(sigma), _p(W), _p(out), _p(ws), wsb, b, c_in, c_out, p_in, p, nn,
+                                               na, ks, _stream()), "epn_inter_so3conv_fwd_f32")
+    return out
+
+
+def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W, need_dfeats=True, need_dw=True):
+    _require_cuda(dout, feats, xyz, centers, idx, anchors, kernels, W)
+    b, _, p_in = xyz.shape
+    p, nn = idx.shape[1], idx.shape[2]
+    na, ks = anchors.shape[0], kernels.shape[0]
+    c_in = 1 if feats is None else feats.shape[1]
+    c_out = W.shape[0]
+    dfeats = (torch.empty(b, c_in, p_in, na, dtype=torch.float32, device=dout.device)
+              if (need_dfeats and feats is not None) else None)
+    dW = torch.empty_like(W) if need_dw else None
+    L = _lib.lib()
+    with torch.cuda.device(dout.device):
+        wsb = L.epn_inter_so3conv_workspace_bytes(b, c_in, c_out, p_in, p, nn, na, ks, 1)
+        ws = _workspace(wsb, dout.device)
+        _lib.check(L.epn_inter_so3conv_bwd_f32(_p(dout), _p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors),
+                                               _p(kernels), float(sigma), _p(W), _p(dfeats), _p(dW), _p(ws), wsb, b,
+                                               c_in, c_out, p_in, p, nn, na, ks, _stream()),
+                   "epn_inter_so3conv_bwd_f32")
+    return dfeats, dW
+
+
+def intra_so3conv_fwd(feats, intra_idx, W):
+    """Fused IntraSO3Conv: feats [b,c,p,na], intra_idx int32 [na,kn], W [co, c*kn] -> [b,co,p,na]."""
+    _require_cuda(feats, intra_idx, W)
+    b, c_in, p, na = feats.shape
+    kn = intra_idx.shape[1]
+    c_out = W.shape[0]
+    if W.shape[1] != c_in * kn:
+        raise RuntimeError("W must be [c_out, c_in*kn]")
+    out = torch.empty(b, c_out, p, na, dtype=torch.float32, device=feats.device)
+    L = _lib.lib()
+    with torch.cuda.device(feats.device):
+        wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 0)
+        ws = _workspace(wsb, feats.device)
+        _lib.check(L.epn_intra_so3conv_fwd_f32(_p(feats), _p(intra_idx), _p(W), _p(out), _p(ws), wsb, b, c_in, c_out,
+                                               p, na, kn, _stream()), "epn_intra_so3conv_fwd_f32")
+    return out
+
+
+def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True):
+    _require_cuda(dout, feats, intra_idx, W)
+    b, c_in, p, na = feats.shape
+    kn = intra_idx.shape[1]
+    c_out = W.shape[0]
+    dfeats = torch.empty_like(feats) if need_dfeats else None
+    dW = torch.empty_like(W) if need_dw else None
+    L = _lib.lib()
+    with torch.cuda.device(feats.device):
+        wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 1)
+        ws = _workspace(wsb, feats.device)
+        _lib.check(L.epn_intra_so3conv_bwd_f32(_p(dout), _p(feats), _p(intra_idx), _p(W), _p(dfeats), _p(dW), _p(ws),
+                                               wsb, b, c_in, c_out, p, na, kn, _stream()),
+                   "epn_intra_so3conv_bwd_f32")
+    return dfeats, dW
+
+
+# ------------------------------------------ drop-in namespaces for vgtk.cuda.*
+grouping = types.SimpleNamespace(ball_query=ball_query, furthest_point_sampling=furthest_point_sampling)
+gathering = types.SimpleNamespace(gather_points_forward=gather_points_forward,
+                                  gather_points_backward=gather_points_backward)
+zpconv = types.SimpleNamespace(inter_zpconv_forward=inter_zpconv_forward,
+                               inter_zpconv_backward=inter_zpconv_backward,
+                               intra_zpconv_forward=intra_zpconv_forward,
+                               intra_zpconv_backward=intra_zpconv_backward)

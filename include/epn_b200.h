@@ -1,0 +1,169 @@
+/*
+ * epn_b200.h -- C ABI of libepn_b200.so, the B200 (sm_100a) engine for the
+ * SE(3) separable point-convolution hot path of nintendops/EPN_PointCloud.
+ *
+ * Drop-in boundary: every entry point replaces one pybind function of the
+ * reference's `vgtk.cuda.*` extensions, or one PyTorch op chain of
+ * `vgtk.so3conv` / `vgtk.spconv` (file:line cited per function; paths are
+ * relative to the reference root, commit b625483).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller; the library never
+ *     allocates, frees or keeps device memory, and holds no global state
+ *     except a thread-local error string;
+ *   - tensors are dense, row-major, in the reference's layouts:
+ *       xyz [B,3,P]   feats [B,C,P,A] (A innermost)   idx [B,P,K] int32
+ *       inter_w [B,P,A,KS,K]   grouped [B,C,KS,P,A]   W [C_out, C_in*KS]
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     every launch goes to that stream; nothing synchronises;
+ *   - return value 0 = success; >0 = cudaError_t of the failed launch;
+ *     <0 = argument check failed (EPN_ERR_*); epn_last_error() describes it.
+ *     No exception ever crosses the boundary.
+ *   - fp32 only (the reference's double dispatch is not on the model path).
+ */
+#ifndef EPN_B200_H_
+#define EPN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPN_B200_VERSION 100 /* major*1000 + minor */
+
+#define EPN_ERR_NULL (-1)     /* required pointer is NULL              */
+#define EPN_ERR_SHAPE (-2)    /* non-positive or unsupported extent    */
+#define EPN_ERR_WORKSPACE (-3) /* workspace too small / missing        */
+#define EPN_ERR_ALIGN (-4)    /* pointer not aligned as required       */
+
+int epn_version(void);
+/* Thread-local, valid until the next failing call on the same thread. */
+const char *epn_last_error(void);
+/* 1 if the library holds a kernel image for the current device (sm_100). */
+int epn_device_supported(void);
+
+/* ------------------------------------------------------------------ grouping
+ * vgtk.cuda.grouping.ball_query  (vgtk/vgtk/cuda/grouping_cuda.cpp:71-86,
+ * kernel grouping_cuda_kernel.cu:67-113).  new_xyz [b,3,m], xyz [b,3,n] ->
+ * idx [b,m,nsample]: first `nsample` support indices (ascending) with
+ * d2 < radius^2 (fp32, FMUL/FFMA/FFMA), cyclic repeat fill if fewer than
+ * nsample-1 hits, a single trailing 0 if exactly nsample-1.  Bit-exact.
+ * Every output slot is written (no pre-zeroing needed). */
+int epn_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *idx, int b, int n, int m,
+                       float radius, int nsample, void *stream);
+
+/* vgtk.cuda.grouping.furthest_point_sampling (grouping_cuda.cpp:160-174,
+ * kernel grouping_cuda_kernel.cu:340-466).  xyz [b,3,n] -> idx [b,m], start at
+ * index 0, points with |p|^2 <= 1e-3 never selected, the reference's
+ * thread/tree tie-breaking reproduced.  Bit-exact.
+ * temp: workspace of epn_fps_workspace_bytes(b,n) bytes (may be NULL when that
+ * returns 0). */
+size_t epn_fps_workspace_bytes(int b, int n);
+int epn_fps_f32(const float *xyz, void *temp, int32_t *idx, int b, int n, int m, void *stream);
+
+/* ----------------------------------------------------------------- gathering
+ * vgtk.cuda.gathering.gather_points_forward / _backward
+ * (gathering_cuda.cpp:29-65, kernels gathering_cuda_kernel.cu:42-98).
+ * points [b,c,n], idx [b,m] -> out [b,c,m];  backward accumulates into
+ * grad_points [b,c,n] which the CALLER must have zeroed. */
+int epn_gather_fwd_f32(const float *points, const int32_t *idx, float *out, int b, int c, int n,
+                       int m, void *stream);
+int epn_gather_bwd_f32(const float *grad_out, const int32_t *idx, float *grad_points, int b, int c,
+                       int n, int m, void *stream);
+
+/* ------------------------------------------------------------ zpconv surface
+ * vgtk.cuda.zpconv.* (zpconv_cuda.cpp:41-118, kernels zpconv_cuda_kernel.cu:32-195).
+ * inter: nbr/w [b,np,na,ks,ann], feats [b,c,nq,na] -> out [b,c,ks,np,na]
+ * intra: nbr [na_out,ann], w [na_out,ks,ann], feats [b,c,np,na_in] -> out [b,c,ks,np,na_out]
+ * Forward outputs are fully written.  Backward outputs are accumulated with
+ * fp32 atomics: the CALLER zeroes dfeats first. */
+int epn_zp_inter_fwd_f32(const int32_t *nbr, const float *w, const float *feats, float *out, int b,
+                         int c, int nq, int np, int na, int ks, int ann, void *stream);
+int epn_zp_inter_bwd_f32(const int32_t *nbr, const float *w, const float *dout, float *dfeats, int b,
+                         int c, int nq, int np, int na, int ks, int ann, void *stream);
+int epn_zp_intra_fwd_f32(const int32_t *nbr, const float *w, const float *feats, float *out, int b,
+                         int c, int np, int na_in, int na_out, int ks, int ann, void *stream);
+int epn_zp_intra_bwd_f32(const int32_t *nbr, const float *w, const float *dout, float *dfeats, int b,
+                         int c, int np, int na_in, int na_out, int ks, int ann, void *stream);
+
+/* ------------------------------------------------- live-path grouping stages
+ * inter_so3conv_grouping_anchor (vgtk/vgtk/so3conv/functional.py:180-218):
+ *   inter_w[b,p,a,k,n] = relu(1 - |xyz[b,:,idx[b,p,n]] - centers[b,:,p] - anchors[a]@kernels[k]|^2 / sigma)
+ * xyz [b,3,p_in], centers [b,3,p], idx [b,p,nn], anchors [na,3,3], kernels [ks,3]. */
+int epn_inter_weights_f32(const float *xyz, const float *centers, const int32_t *idx,
+                          const float *anchors, const float *kernels, float sigma, float *inter_w,
+                          int b, int p_in, int p, int nn, int na, int ks, void *stream);
+
+/* inter_zpconv_grouping_naive (vgtk/vgtk/spconv/functional.py:372-390):
+ *   out[b,c,k,p,a] = sum_n feats[b,c,idx[b,p,n],a] * inter_w[b,p,a,k,n]
+ * If inter_w == NULL the weights are recomputed on the fly from
+ * (xyz, centers, anchors, kernels, sigma) and never touch HBM. */
+int epn_inter_group_fwd_f32(const float *feats, const int32_t *idx, const float *inter_w,
+                            const float *xyz, const float *centers, const float *anchors,
+                            const float *kernels, float sigma, float *out, int b, int c, int p_in,
+                            int p, int nn, int na, int ks, void *stream);
+/* adjoint w.r.t. feats; dfeats [b,c,p_in,na] must be zeroed by the caller. */
+int epn_inter_group_bwd_f32(const float *dout, const int32_t *idx, const float *inter_w,
+                            const float *xyz, const float *centers, const float *anchors,
+                            const float *kernels, float sigma, float *dfeats, int b, int c,
+                            int p_in, int p, int nn, int na, int ks, void *stream);
+
+/* intra_so3conv_grouping (vgtk/vgtk/so3conv/functional.py:221-268):
+ *   out[b,c,k,p,a] = feats[b,c,p,intra_idx[a,k]];  intra_idx [na,kn] int32.
+ * Backward: dfeats [b,c,p,na] fully written (no atomics, no pre-zeroing);
+ * requires every column of intra_idx to be a permutation (true for the
+ * icosahedral index) -- otherwise use epn_zp_intra_bwd_f32. */
+int epn_intra_group_fwd_f32(const float *feats, const int32_t *intra_idx, float *out, int b, int c,
+                            int p, int na, int kn, void *stream);
+int epn_intra_group_bwd_f32(const float *dout, const int32_t *intra_idx, float *dfeats, int b, int c,
+                            int p, int na, int kn, void *stream);
+
+/* ------------------------------------------------------------- fused convs
+ * InterSO3Conv.forward minus sampling/ball query
+ * (vgtk/vgtk/so3conv/modules.py:157-174 = so3conv/functional.py:174-176 +
+ * modules.py:48-55):
+ *   out[b,o,p,a] = sum_{c,k} W[o,c*ks+k] * sum_n w(b,p,a,k,n) * feats[b,c,idx[b,p,n],a]
+ * feats == NULL means feats == 1 with c_in == 1 (layer 0: occupancy features,
+ * so3conv/functional.py:25-44).  inter_w is never materialised.
+ * workspace: epn_inter_so3conv_workspace_bytes(...) bytes, 256-B aligned. */
+size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int p_in, int p, int nn, int na,
+                                         int ks, int backward);
+int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
+                              const int32_t *idx, const float *anchors, const float *kernels,
+                              float sigma, const float *W, float *out, void *workspace,
+                              size_t workspace_bytes, int b, int c_in, int c_out, int p_in, int p,
+                              int nn, int na, int ks, void *stream);
+/* dout [b,c_out,p,na] -> dfeats [b,c_in,p_in,na] (NULL to skip; else fully
+ * written) and dW [c_out,c_in*ks] (NULL to skip; else fully written). */
+int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, const float *xyz,
+                              const float *centers, const int32_t *idx, const float *anchors,
+                              const float *kernels, float sigma, const float *W, float *dfeats,
+                              float *dW, void *workspace, size_t workspace_bytes, int b, int c_in,
+                              int c_out, int p_in, int p, int nn, int na, int ks, void *stream);
+
+/* IntraSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:197-200):
+ *   out[b,o,p,a] = sum_{c,k} W[o,c*kn+k] * feats[b,c,p,intra_idx[a,k]] */
+size_t epn_intra_so3conv_workspace_bytes(int b, int c_in, int c_out, int p, int na, int kn,
+                                         int backward);
+int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
+                              void *workspace, size_t workspace_bytes, int b, int c_in, int c_out,
+                              int p, int na, int kn, void *stream);
+int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
+                              const float *W, float *dfeats, float *dW, void *workspace,
+                              size_t workspace_bytes, int b, int c_in, int c_out, int p, int na,
+                              int kn, void *stream);
+
+/* BasicSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:48-55) on an already
+ * grouped tensor: x [b, ck, pa], W [co, ck] -> out [b, co, pa]. */
+int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, int b, int ck, int co, int pa,
+                           void *stream);
+/* dx [b,ck,pa] (NULL to skip), dW [co,ck] (NULL to skip; fully written). */
+int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, float *dx, float *dW,
+                           int b, int ck, int co, int pa, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPN_B200_H_ */

@@ -1,0 +1,157 @@
+"""CPU restatement ("port") of the reference's PyTorch op chains for the SPConv hot path.
+
+TEST INFRASTRUCTURE ONLY -- the parity checker and the CPU baseline.  Only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this;
+the product package `epn_pointcloud_b200` never does.
+
+It keeps the reference's op chain (torch.gather -> broadcast weights -> einsum -> matmul;
+index_select -> permute -> matmul; norm -> leaky_relu -> skip) so that timing it on host
+cores measures what the reference's own CPU path costs, and its numerics are fp32 like
+the reference.  The three native index ops come from the C oracle (oracle/epn_oracle.c).
+Pinned against the real reference by oracle/make_golden.py (tests/golden/*.npz).
+
+Each function cites the reference file:line it follows (nintendops/EPN_PointCloud @ b625483).
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from oracle import epn_oracle as O
+
+
+# ------------------------------------------------------------------ sampling
+def sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample):
+    """vgtk/vgtk/spconv/functional.py:412-421 + vgtk/vgtk/pc/sample.py:46-77.
+    xyz [b,3,p_in] -> (grouped_xyz - centre [b,3,p,nn], ball_idx [b,p,nn], sample_idx [b,p], new_xyz [b,3,p])"""
+    b, _, p_in = xyz.shape
+    n_sample = math.ceil(p_in / stride)
+    if p_in == n_sample or lazy_sample:
+        sample_idx = torch.arange(n_sample, dtype=torch.int32).view(1, -1).expand(b, -1).contiguous()
+    else:
+        sample_idx = O.furthest_point_sampling(xyz, n_sample)
+    new_xyz = O.gather_points_forward(xyz, sample_idx)
+    ball_idx = O.ball_query(new_xyz, xyz, radius, n_neighbor)
+    grouped = O.gather_points_forward(xyz, ball_idx.view(b, -1)).view(b, 3, n_sample, n_neighbor)
+    return grouped - new_xyz.unsqueeze(3), ball_idx, sample_idx, new_xyz
+
+
+# ------------------------------------------------------------ kernel weights
+def inter_weights(grouped_xyz, anchors, kernels, sigma):
+    """vgtk/vgtk/so3conv/functional.py:180-218: rotate kernel points by every anchor, squared
+    distance to every neighbour offset, linear falloff clipped at 0 -> [b,p,na,ks,nn]."""
+    rk = torch.matmul(anchors, kernels.t())                 # [na,3,ks]
+    rk = rk.permute(1, 0, 2).contiguous()                   # [3,na,ks]
+    diff = grouped_xyz[:, :, :, None, None, :] - rk[None, :, None, :, :, None]   # [b,3,p,na,ks,nn]
+    dist2 = (diff ** 2).sum(dim=1)
+    return F.relu(1.0 - dist2 / sigma)
+
+
+# ------------------------------------------------------------ feature grouping
+def inter_group(inter_idx, inter_w, feats):
+    """vgtk/vgtk/spconv/functional.py:361-390: expanded-index gather of the neighbours' feature rows,
+    then the per-anchor spatial contraction over the nn neighbours -> [b,c,ks,p,na]."""
+    b, p, nn_ = inter_idx.shape
+    _, c, q, a = feats.shape
+    index = inter_idx.long().view(b, 1, p * nn_, 1).expand(b, c, p * nn_, a)
+    g = torch.gather(feats, 2, index).view(b, c, p, nn_, a)
+    return torch.einsum("bcpna,bpakn->bckpa", g, inter_w).contiguous()
+
+
+def intra_group(intra_idx, feats):
+    """vgtk/vgtk/so3conv/functional.py:221-268 -> [b,c,kn,p,na]"""
+    b, c, p, na = feats.shape
+    kn = intra_idx.shape[1]
+    g = feats.index_select(3, intra_idx.long().reshape(-1)).view(b, c, p, na, kn)
+    return g.permute(0, 1, 4, 2, 3).contiguous()
+
+
+def basic_conv(x, W):
+    """vgtk/vgtk/so3conv/modules.py:48-55"""
+    b, c, ks, p, a = x.shape
+    return torch.matmul(W, x.view(b, c * ks, p * a)).view(b, W.shape[0], p, a)
+
+
+# ----------------------------------------------------------------- conv layers
+def inter_so3conv(xyz, feats, W, anchors, kernels, stride, n_neighbor, radius, sigma, lazy_sample=True):
+    """InterSO3Conv.forward: vgtk/vgtk/so3conv/modules.py:157-174 -> so3conv/functional.py:118-178
+    (incl. the zero shadow row appended at :174, spconv/functional.py:91-95).
+    Returns (inter_idx, inter_w, sample_idx, new_xyz, out)."""
+    grouped_xyz, inter_idx, sample_idx, new_xyz = sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample)
+    inter_w = inter_weights(grouped_xyz, anchors, kernels, sigma)
+    b, c, _, a = feats.shape
+    feats_sh = torch.cat((feats, torch.zeros(b, c, 1, a)), dim=2).contiguous()
+    grouped = inter_group(inter_idx, inter_w, feats_sh)
+    return inter_idx, inter_w, sample_idx, new_xyz, basic_conv(grouped, W)
+
+
+def intra_so3conv(feats, W, intra_idx):
+    """IntraSO3Conv.forward: vgtk/vgtk/so3conv/modules.py:197-200"""
+    return basic_conv(intra_group(intra_idx, feats), W)
+
+
+# ---------------------------------------------------------------------- blocks
+def _norm(x, kind, weight=None, bias=None, eps=1e-5):
+    """BatchNorm2d in training mode (batch statistics) or InstanceNorm2d(affine=False);
+    SPConvNets/utils/base_so3conv.py:43,107,193."""
+    if kind == "BatchNorm2d":
+        return F.batch_norm(x, None, None, weight, bias, True, 0.1, eps)
+    return F.instance_norm(x, eps=eps)
+
+
+def separable_block(xyz, feats, prm, args, intra_idx, anchors, kernels):
+    """SeparableSO3ConvBlock.forward (SPConvNets/utils/base_so3conv.py:197-212) with the
+    InterSO3ConvBlock (:116-126) and IntraSO3ConvBlock (:52-62) it calls; training mode, dropout 0.
+    prm: dict of tensors {inter_W, inter_bn_w, inter_bn_b, intra_W, skip_w, skip_b, bn_w, bn_b}."""
+    norm = args.get("norm")
+    skip = feats
+    _, _, sample_idx, new_xyz, x = inter_so3conv(xyz, feats, prm["inter_W"], anchors, kernels, args["stride"],
+                                                 args["n_neighbor"], args["radius"], args["sigma"],
+                                                 args["lazy_sample"])
+    x = F.leaky_relu(_norm(x, norm, prm.get("inter_bn_w"), prm.get("inter_bn_b")))
+    if intra_idx is not None:
+        x = intra_so3conv(x, prm["intra_W"], intra_idx)
+        x = F.leaky_relu(_norm(x, None))
+    if args["stride"] > 1:
+        b, c, _, a = skip.shape
+        index = sample_idx.long().view(b, 1, -1, 1).expand(b, c, sample_idx.shape[1], a)
+        skip = torch.gather(skip, 2, index)
+    skip = F.conv2d(skip, prm["skip_w"], prm["skip_b"])
+    skip = F.leaky_relu(_norm(skip, norm, prm.get("bn_w"), prm.get("bn_b")))
+    return new_xyz, x + skip
+
+
+def backbone_forward(x, layers):
+    """ClsSO3ConvModel.forward minus the head (SPConvNets/models/cls_so3net_pn.py:27-33;
+    preprocess_input base_so3conv.py:16-23 with add_center=False).
+    x [b,n,3]; layers: list of (prm, args, intra_idx, anchors, kernels)."""
+    b, n, _ = x.shape
+    xyz = x.permute(0, 2, 1).contiguous()
+    na = layers[0][3].shape[0]
+    feats = torch.ones(b, 1, n, na)
+    for prm, args, intra_idx, anchors, kernels in layers:
+        xyz, feats = separable_block(xyz, feats, prm, args, intra_idx, anchors, kernels)
+    return xyz, feats
+
+
+def layers_from_module(backbone):
+    """Pull (prm, args, ...) out of an `epn_pointcloud_b200.blocks.SO3ConvBackbone` (or the
+    reference's ModuleList of BasicSO3ConvBlock) living on any device -> CPU tensors."""
+    layers = []
+    for blk in backbone.backbone:
+        for conv, param in zip(blk.blocks, blk.params):
+            assert param["type"] == "separable_block"
+            sd = {k: v.detach().cpu().float() for k, v in conv.state_dict().items()}
+            prm = {"inter_W": sd["inter_conv.conv.basic_conv.W"], "skip_w": sd["skip_conv.weight"],
+                   "skip_b": sd["skip_conv.bias"]}
+            if "inter_conv.norm.weight" in sd:
+                prm["inter_bn_w"], prm["inter_bn_b"] = sd["inter_conv.norm.weight"], sd["inter_conv.norm.bias"]
+            if "norm.weight" in sd:
+                prm["bn_w"], prm["bn_b"] = sd["norm.weight"], sd["norm.bias"]
+            intra_idx = None
+            if "intra_conv.conv.basic_conv.W" in sd:
+                prm["intra_W"] = sd["intra_conv.conv.basic_conv.W"]
+                intra_idx = conv.state_dict()["intra_conv.conv.intra_idx"].cpu()
+            layers.append((prm, param["args"], intra_idx, sd["inter_conv.conv.anchors"],
+                           sd["inter_conv.conv.kernels"]))
+    return layers
