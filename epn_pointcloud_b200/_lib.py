@@ -52,6 +52,9 @@ SIGNATURES = {
     "epn_version": (c_i, []),
     "epn_last_error": (ctypes.c_char_p, []),
     "epn_device_supported": (c_i, []),
+    "epn_launch_count": (ctypes.c_ulonglong, []),
+    "epn_profile_enable": (None, [c_i]),
+    "epn_profile_read": (c_i, [c_f, c_f, c_i]),
     "epn_ball_query_f32": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_fl, c_i, c_f]),
     "epn_fps_workspace_bytes": (c_sz, [c_i, c_i]),
     "epn_fps_f32": (c_i, [c_f, c_f, c_f, c_i, c_i, c_i, c_f]),

@@ -11,6 +11,7 @@
 namespace epn {
 
 void set_error(const char *fmt, ...);
+void count_launch();
 
 inline int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
@@ -18,8 +19,28 @@ inline int check_launch(const char *what) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return (int)e;
     }
+    count_launch();
     return 0;
 }
+
+// Kernel classes for the optional per-kernel CUDA-event timing (epn_profile_*).
+enum KernelClass {
+    KC_INDEX = 0,        // ball query, FPS, gather
+    KC_INTER_GROUP = 1,  // inter grouping fwd (gather + kernel weights + spatial contraction)
+    KC_INTER_SCATTER = 2,// inter grouping bwd (transposed contraction + RED scatter)
+    KC_INTRA_GROUP = 3,  // intra grouping fwd/bwd
+    KC_GEMM = 4,         // channel GEMMs (fwd, dX, dW)
+    KC_OTHER = 5,
+    KC_COUNT = 6
+};
+
+// RAII: brackets the launches issued in its scope with a cudaEvent pair when profiling is on.
+struct ProfScope {
+    cudaStream_t s;
+    void *slot;
+    ProfScope(cudaStream_t stream, int kclass);
+    ~ProfScope();
+};
 
 #define EPN_REQUIRE_PTR(p)                                \
     do {                                                  \

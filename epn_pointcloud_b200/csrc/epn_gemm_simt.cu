@@ -88,6 +88,7 @@ int launch_sgemm(const GemmOperand &A, const GemmOperand &B, float *C, long long
         set_error("sgemm: grid too large (M=%d batch*split=%d)", M, batch * split_k);
         return EPN_ERR_SHAPE;
     }
+    ProfScope prof(s, KC_GEMM);
     sgemm_kernel<<<grid, 256, 0, s>>>(A, B, C, c_stride_z, ldc, M, N, K, split_k, accumulate);
     return check_launch("sgemm_kernel");
 }

@@ -448,6 +448,7 @@ int launch_inter_group_fwd(const float *feats, const int32_t *idx, const float *
                            float *out, long long stride_b, long long stride_ck, int p_off, int p_cnt, int b,
                            int c, int p_in, int p, int nn, int na, int ks, cudaStream_t s) {
     GroupOut o{out, stride_b, stride_ck, p_off, p_cnt};
+    ProfScope prof(s, KC_INTER_GROUP);
     const size_t smem = (size_t)nn * 4 * sizeof(float);
     dim3 grid(p_cnt, b);
     if (nn <= 16) {
@@ -464,6 +465,7 @@ int launch_inter_group_bwd(const float *dgrouped, long long stride_b, long long 
                            const int32_t *idx, const float *inter_w, const InterGeom &g, float *dfeats, int b,
                            int c, int p_in, int p, int nn, int na, int ks, cudaStream_t s) {
     const size_t smem = (size_t)nn * 4 * sizeof(float);
+    ProfScope prof(s, KC_INTER_SCATTER);
     dim3 grid(p_cnt, b);
     const int groups = min(8, cdiv(nn, 4));
     inter_group_bwd_kernel<24, 4><<<grid, ALANES * groups, smem, s>>>(dgrouped, stride_b, stride_ck, p_off, p_cnt, idx,
@@ -475,6 +477,7 @@ int launch_intra_group_fwd(const float *feats, const int32_t *intra_idx, float *
                            long long stride_ck, int p_off, int p_cnt, int b, int c, int p, int na, int kn,
                            cudaStream_t s) {
     IntraOut o{out, stride_b, stride_ck, p_off, p_cnt};
+    ProfScope prof(s, KC_INTRA_GROUP);
     const int rows = 4;
     dim3 block(64, rows);
     const size_t smem = ((size_t)na * kn + (size_t)rows * na) * sizeof(float);
@@ -486,6 +489,7 @@ int launch_intra_group_fwd(const float *feats, const int32_t *intra_idx, float *
 int launch_intra_group_bwd(const float *dgrouped, long long stride_b, long long stride_ck, int p_off, int p_cnt,
                            const int32_t *intra_idx, float *dfeats, int b, int c, int p, int na, int kn,
                            cudaStream_t s) {
+    ProfScope prof(s, KC_INTRA_GROUP);
     const int rows = 4;
     dim3 block(64, rows);
     const size_t smem = (size_t)na * kn * sizeof(int32_t);

@@ -3,11 +3,42 @@
 // vgtk.cuda.gathering.gather_points_{forward,backward} of the reference.
 #include <stdarg.h>
 
+#include <atomic>
+#include <mutex>
+#include <vector>
+
 #include "epn_common.cuh"
 
 namespace epn {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- optional per-kernel-class timing (off by default; bench.py turns it on for one pass)
+struct ProfSlot { cudaEvent_t a, b; int kclass; };
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfSlot *> g_prof_slots;
+
+ProfScope::ProfScope(cudaStream_t stream, int kclass) : s(stream), slot(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfSlot *p = new ProfSlot;
+    p->kclass = kclass;
+    cudaEventCreate(&p->a);
+    cudaEventCreate(&p->b);
+    cudaEventRecord(p->a, s);
+    slot = p;
+}
+
+ProfScope::~ProfScope() {
+    if (slot == nullptr) return;
+    ProfSlot *p = static_cast<ProfSlot *>(slot);
+    cudaEventRecord(p->b, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_slots.push_back(p);
+}
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -195,6 +226,34 @@ EPN_API int epn_version(void) { return EPN_B200_VERSION; }
 
 EPN_API const char *epn_last_error(void) { return g_err; }
 
+EPN_API unsigned long long epn_launch_count(void) { return g_launches.load(); }
+
+EPN_API void epn_profile_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+EPN_API int epn_profile_read(double *ms_per_class, long long *scopes_per_class, int n_class) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (int i = 0; i < n_class; ++i) {
+        if (ms_per_class) ms_per_class[i] = 0.0;
+        if (scopes_per_class) scopes_per_class[i] = 0;
+    }
+    int rc = 0;
+    for (ProfSlot *p : g_prof_slots) {
+        float ms = 0.f;
+        cudaError_t e = cudaEventSynchronize(p->b);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, p->a, p->b);
+        if (e != cudaSuccess) { set_error("epn_profile_read: %s", cudaGetErrorString(e)); rc = (int)e; }
+        if (p->kclass >= 0 && p->kclass < n_class) {
+            if (ms_per_class) ms_per_class[p->kclass] += ms;
+            if (scopes_per_class) scopes_per_class[p->kclass] += 1;
+        }
+        cudaEventDestroy(p->a);
+        cudaEventDestroy(p->b);
+        delete p;
+    }
+    g_prof_slots.clear();
+    return rc;
+}
+
 EPN_API int epn_device_supported(void) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
@@ -212,6 +271,7 @@ EPN_API int epn_ball_query_f32(const float *new_xyz, const float *xyz, int32_t *
     const float r2 = radius * radius;  // fp32, as the reference (grouping_cuda_kernel.cu:83)
     dim3 grid(cdiv(m, BQ_WARPS), b);
     const size_t smem = (size_t)BQ_WARPS * nsample * sizeof(int32_t);
+    ProfScope prof(as_stream(stream), KC_INDEX);
     ball_query_kernel<<<grid, BQ_WARPS * 32, smem, as_stream(stream)>>>(new_xyz, xyz, idx, n, m, r2, nsample);
     return check_launch("ball_query_kernel");
 }
@@ -230,6 +290,7 @@ EPN_API int epn_fps_f32(const float *xyz, void *temp, int32_t *idx, int b, int n
     const int threads = T < 32 ? 32 : T;
     const int ppt = cdiv(n, T);
     cudaStream_t s = as_stream(stream);
+    ProfScope prof(s, KC_INDEX);
     float *tw = static_cast<float *>(temp);
 #define EPN_FPS(P) fps_kernel<P><<<b, threads, 0, s>>>(xyz, tw, idx, n, m, T, logT)
     if (ppt <= 1) EPN_FPS(1);
@@ -251,6 +312,7 @@ EPN_API int epn_gather_fwd_f32(const float *points, const int32_t *idx, float *o
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c); EPN_REQUIRE_POS(n); EPN_REQUIRE_POS(m);
     EPN_REQUIRE(b <= 65535, EPN_ERR_SHAPE, "batch > 65535");
     dim3 grid(cdiv(m, 256), c < 64 ? c : 64, b);
+    ProfScope prof(as_stream(stream), KC_INDEX);
     gather_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(points, idx, out, c, n, m);
     return check_launch("gather_fwd_kernel");
 }

@@ -43,6 +43,16 @@ int epn_version(void);
 const char *epn_last_error(void);
 /* 1 if the library holds a kernel image for the current device (sm_100). */
 int epn_device_supported(void);
+/* Number of kernels this library has launched in this process (all threads). */
+unsigned long long epn_launch_count(void);
+/* Optional per-kernel-class device timing (bench.py's roofline pass; off by default).
+ * While enabled every launch site is bracketed by a cudaEvent pair on its stream.
+ * epn_profile_read synchronises on the recorded events, sums their elapsed ms per class
+ * into ms_per_class[0..n_class) / scopes_per_class[0..n_class) and clears the record.
+ * Classes: 0 index ops, 1 inter grouping fwd, 2 inter grouping bwd (scatter),
+ * 3 intra grouping, 4 channel GEMMs, 5 other. */
+void epn_profile_enable(int on);
+int epn_profile_read(double *ms_per_class, long long *scopes_per_class, int n_class);
 
 /* ------------------------------------------------------------------ grouping
  * vgtk.cuda.grouping.ball_query  (vgtk/vgtk/cuda/grouping_cuda.cpp:71-86,

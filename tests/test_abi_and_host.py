@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/epn_b200.h declares;
+host-side logic (sharding, flat-gradient all-reduce over gloo, error behaviour without a GPU)."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "epn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(epn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from epn_pointcloud_b200 import _lib
+    so = _lib.build()
+    assert os.path.exists(so)
+    lib = ctypes.CDLL(so)
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(lib, name), "header declares %s but the library does not export it" % name
+    assert sorted(_lib.SIGNATURES) == declared, "python SIGNATURES table out of sync with the header"
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", so]).decode()
+    extra = [l.split()[-1] for l in exported.splitlines() if " T " in l and not l.split()[-1].startswith("epn_")]
+    assert extra == [] or all(e.startswith("_") for e in extra), extra
+
+
+def test_version_and_argument_errors_without_gpu():
+    from epn_pointcloud_b200 import _lib
+    L = _lib.lib()
+    assert L.epn_version() == 100
+    # NULL pointers and bad extents are rejected before anything touches a device
+    rc = L.epn_ball_query_f32(None, None, None, 1, 8, 8, 0.1, 4, None)
+    assert rc == -1 and b"NULL" in L.epn_last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = L.epn_ball_query_f32(p, p, p, 0, 8, 8, 0.1, 4, None)
+    assert rc == -2 and b"must be > 0" in L.epn_last_error()
+    rc = L.epn_inter_so3conv_fwd_f32(None, p, p, p, p, p, 0.1, p, p, p, 16, 1, 4, 4, 8, 8, 4, 60, 24, None)
+    assert rc == -1  # feats NULL with c_in != 1
+    assert L.epn_inter_so3conv_workspace_bytes(2, 4, 8, 64, 64, 16, 60, 24, 0) == 2 * 4 * 24 * 64 * 60 * 4
+    assert L.epn_fps_workspace_bytes(4, 1024) == 0 and L.epn_fps_workspace_bytes(4, 20000) == 4 * 20000 * 4
+
+
+def test_product_path_refuses_cpu_tensors():
+    from epn_pointcloud_b200 import ops
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.ball_query(torch.zeros(1, 3, 8), torch.zeros(1, 3, 8), 0.1, 4)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        ops.intra_so3conv_fwd(torch.zeros(1, 2, 4, 60), torch.zeros(60, 12, dtype=torch.int32), torch.zeros(3, 24))
+
+
+def test_product_package_never_imports_the_oracle():
+    for fn in os.listdir(os.path.join(ROOT, "epn_pointcloud_b200")):
+        if fn.endswith(".py"):
+            src = open(os.path.join(ROOT, "epn_pointcloud_b200", fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_shard_ranges():
+    from epn_pointcloud_b200.parallel import shard_pairs, shard_range
+    for n, ws in ((32, 8), (32, 3), (5, 8), (16, 2)):
+        spans = [shard_range(n, r, ws) for r in range(ws)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(ws - 1))
+        sizes = [hi - lo for lo, hi in spans]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_pairs(32, 1, 8) == (8, 16)
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from epn_pointcloud_b200.parallel import FlatGradSync, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+torch.manual_seed(0)
+model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+sync = FlatGradSync(model.parameters())
+x = torch.arange(8 * 6, dtype=torch.float32).view(8, 6) / 10
+lo, hi = shard_range(8, dist.get_rank(), 2)
+sync.zero()
+model(x[lo:hi]).pow(2).sum().backward()
+sync.all_reduce_mean()
+ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+ref.load_state_dict(model.state_dict())
+(ref(x).pow(2).sum() / 2).backward()
+for p, q in zip(model.parameters(), ref.parameters()):
+    assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
+    assert p.grad.data_ptr() >= sync.flat.data_ptr()
+dist.destroy_process_group()
+print("ok")
+"""
+
+
+def test_flat_grad_all_reduce_gloo_world2(tmp_path):
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, str(port), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, o

@@ -1,0 +1,375 @@
+"""GPU (B200) parity tests: the CUDA path, called through the C ABI (epn_pointcloud_b200.ops ->
+libepn_b200.so), against (1) the CPU oracle on the same seeded inputs, (2) the golden fixtures
+produced by the reference's own Python, (3) the reference's own CUDA kernels rebuilt into
+oracle/_ref (index ops + zpconv surface), and (4) size-independent properties at BASELINE sizes.
+
+Bars: bit-exact for indices; <= 1e-4 relative (max|a-b| / max|b|) for fp32 features and gradients.
+"""
+import math
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FEAT_TOL = 1e-4   # north_star: "within 1e-4 relative fp32 for features"
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def E():
+    import epn_pointcloud_b200 as pkg
+    from epn_pointcloud_b200 import _lib
+    assert _lib.lib().epn_device_supported() == 1, "libepn_b200.so holds sm_100a code only"
+    return pkg
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import epn_oracle
+    epn_oracle.lib()
+    return epn_oracle
+
+
+def sphere(b, n, seed, surface=True):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, 3, n, generator=g)
+    if surface:
+        x = x / x.norm(dim=1, keepdim=True)
+    else:
+        x = x / x.norm(dim=1, keepdim=True) * torch.rand(b, 1, n, generator=g) ** (1 / 3)
+    return x.contiguous()
+
+
+def cuda(*ts):
+    return [t.to(DEV) if t is not None else None for t in ts]
+
+
+# ----------------------------------------------------------------- index ops
+@pytest.mark.parametrize("b,n,m,radius,k", [
+    (2, 1024, 512, 0.2, 32), (3, 500, 500, 0.35, 16), (1, 97, 33, 0.6, 64), (2, 256, 256, 0.05, 8),
+    (1, 2048, 512, 0.4, 128), (2, 64, 64, 3.0, 16), (1, 40, 40, 0.3, 1),
+])
+def test_ball_query_bit_exact_vs_oracle(E, O, b, n, m, radius, k):
+    xyz = sphere(b, n, 100 + n)
+    q = xyz[:, :, :m].contiguous()
+    got = E.ops.ball_query(q.to(DEV), xyz.to(DEV), radius, k).cpu()
+    assert torch.equal(got, O.ball_query(q, xyz, radius, k))
+
+
+def test_ball_query_fill_rule_edge_cases(E, O):
+    # cnt == 0 (query far away), cnt == nsample-1 (trailing 0), cnt < nsample-1 (cyclic fill), cnt >= nsample
+    xyz = torch.zeros(1, 3, 12)
+    xyz[0, 0] = torch.arange(12) * 0.1
+    q = torch.tensor([[[50.0, 0.35, 0.0, 1.1]], [[0.0] * 4], [[0.0] * 4]]).view(1, 3, 4)
+    for k in (1, 2, 3, 4, 5, 8):
+        got = E.ops.ball_query(q.to(DEV), xyz.to(DEV), 0.21, k).cpu()
+        want = O.ball_query(q, xyz, 0.21, k)
+        assert torch.equal(got, want), (k, got, want)
+    assert E.ops.ball_query(q.to(DEV), xyz.to(DEV), 0.21, 5).cpu()[0, 0].tolist() == [0] * 5       # cnt == 0
+    assert E.ops.ball_query(q.to(DEV), xyz.to(DEV), 0.21, 5).cpu()[0, 1].tolist() == [2, 3, 4, 5, 0]  # cnt == k-1
+
+
+@pytest.mark.parametrize("b,n,m", [(2, 1024, 512), (3, 300, 64), (1, 2048, 512), (2, 5000, 256), (1, 31, 10),
+                                    (1, 20000, 64)])
+def test_fps_bit_exact_vs_oracle(E, O, b, n, m):
+    xyz = sphere(b, n, 200 + n, surface=False)
+    xyz[:, :, 5] = 0.001      # |p|^2 <= 1e-3: never selected (grouping_cuda_kernel.cu:385-387)
+    xyz[:, :, 7] = xyz[:, :, 3]  # duplicate point: exercises the tie-breaking order
+    got = E.ops.furthest_point_sampling(xyz.to(DEV), m).cpu()
+    assert torch.equal(got, O.furthest_point_sampling(xyz, m))
+
+
+def test_fps_ties_on_a_lattice(E, O):
+    # integer lattice -> massive exact ties; the reference's thread/tree order decides
+    g = torch.stack(torch.meshgrid(torch.arange(8.0), torch.arange(8.0), torch.arange(8.0), indexing="ij"), 0)
+    xyz = (g.reshape(1, 3, 512) + 1.0).contiguous()
+    got = E.ops.furthest_point_sampling(xyz.to(DEV), 200).cpu()
+    assert torch.equal(got, O.furthest_point_sampling(xyz, 200))
+
+
+def test_index_ops_bit_exact_vs_reference_cuda_kernels(E):
+    """Pins the oracle's FMA-order assumption against the reference's own kernels on this GPU."""
+    from oracle import build_ref
+    ref = build_ref.load_ref("grouping")
+    if ref is None:
+        pytest.skip("oracle/_ref not built (build container only)")
+    for seed, (b, n, m, radius, k) in enumerate([(4, 1024, 512, 0.2, 32), (2, 512, 512, 0.2828, 16),
+                                                (2, 2048, 512, 0.08, 128), (3, 333, 111, 0.5, 24)]):
+        xyz = sphere(b, n, 300 + seed).to(DEV)
+        sidx_ref = ref.furthest_point_sampling(xyz, m)
+        sidx = E.ops.furthest_point_sampling(xyz, m)
+        assert torch.equal(sidx, sidx_ref)
+        q = E.ops.gather_points_forward(xyz, sidx)
+        assert torch.equal(E.ops.ball_query(q, xyz, radius, k), ref.ball_query(q, xyz, radius, k))
+    gref = build_ref.load_ref("gathering")
+    pts = torch.randn(2, 5, 100, device=DEV)
+    idx = torch.randint(0, 100, (2, 37), device=DEV, dtype=torch.int32)
+    assert torch.equal(E.ops.gather_points_forward(pts, idx), gref.gather_points_forward(pts, idx))
+    g = torch.randn(2, 5, 37, device=DEV)
+    assert rel_err(E.ops.gather_points_backward(g, idx, 100), gref.gather_points_backward(g, idx, 100)) < 1e-6
+
+
+def test_gather_fwd_bwd(E, O):
+    pts = torch.randn(3, 7, 129)
+    idx = torch.randint(0, 129, (3, 300), dtype=torch.int32)
+    assert torch.equal(E.ops.gather_points_forward(pts.to(DEV), idx.to(DEV)).cpu(), O.gather_points_forward(pts, idx))
+    g = torch.randn(3, 7, 300)
+    assert rel_err(E.ops.gather_points_backward(g.to(DEV), idx.to(DEV), 129), O.gather_points_backward(g, idx, 129)) < 1e-6
+
+
+# ------------------------------------------------------------- zpconv surface
+def _zp_inputs():
+    g = torch.Generator().manual_seed(5)
+    b, c, nq, np_, na, ks, ann = 2, 3, 20, 9, 12, 5, 4
+    nbr = torch.randint(0, nq, (b, np_, na, ks, ann), generator=g, dtype=torch.int32)
+    w = torch.rand(b, np_, na, ks, ann, generator=g)
+    feats = torch.randn(b, c, nq, na, generator=g)
+    dout = torch.randn(b, c, ks, np_, na, generator=g)
+    inbr = torch.randint(0, 10, (na, ann), generator=g, dtype=torch.int32)
+    iw = torch.rand(na, ks, ann, generator=g)
+    ifeats = torch.randn(b, c, np_, 10, generator=g)
+    return nbr, w, feats, dout, inbr, iw, ifeats
+
+
+def test_zpconv_surface_vs_oracle_and_reference_kernels(E, O):
+    nbr, w, feats, dout, inbr, iw, ifeats = _zp_inputs()
+    z = E.ops.zpconv
+    got = [z.inter_zpconv_forward(*cuda(nbr, w, feats)), z.inter_zpconv_backward(*cuda(nbr, w, dout), 20),
+           z.intra_zpconv_forward(*cuda(inbr, iw, ifeats)), z.intra_zpconv_backward(*cuda(inbr, iw, dout), 10)]
+    want = [O.zp_inter_forward(nbr, w, feats), O.zp_inter_backward(nbr, w, dout, 20),
+            O.zp_intra_forward(inbr, iw, ifeats), O.zp_intra_backward(inbr, iw, dout, 10)]
+    for a, b_ in zip(got, want):
+        assert a.shape == b_.shape and rel_err(a, b_) < 1e-5
+    from oracle import build_ref
+    ref = build_ref.load_ref("zpconv")
+    if ref is not None:
+        rgot = [ref.inter_zpconv_forward(*cuda(nbr, w, feats)), ref.inter_zpconv_backward(*cuda(nbr, w, dout), 20),
+                ref.intra_zpconv_forward(*cuda(inbr, iw, ifeats)), ref.intra_zpconv_backward(*cuda(inbr, iw, dout), 10)]
+        for a, b_ in zip(got, rgot):
+            assert rel_err(a, b_) < 1e-5
+
+
+# ------------------------------------------------------------ grouping stages
+def test_inter_weights_and_grouping_vs_golden(E):
+    g = load_golden("inter_group")
+    xyz = g["pc"].permute(0, 2, 1).contiguous().to(DEV)
+    anchors, kernels, feats = cuda(g["anchors"], g["kernels"], g["feats"])
+    sigma = float(g["sigma"])
+    idx = E.ops.ball_query(xyz, xyz, 0.5, 12)
+    assert torch.equal(idx.cpu(), g["ball_idx"])
+    w = E.ops.inter_weights(xyz, xyz, idx, anchors, kernels, sigma)
+    assert rel_err(w, g["inter_w"]) < 1e-5
+    w2 = E.functional.inter_so3conv_grouping_anchor(g["grouped_xyz"].to(DEV), anchors, kernels, sigma)
+    assert rel_err(w2, g["inter_w"]) < 1e-5
+    geom = (xyz, xyz, anchors, kernels, sigma)
+    for kw in ({"inter_w": w}, {"geom": geom}):
+        assert rel_err(E.ops.inter_group_fwd(feats, idx, **kw), g["grouped"]) < FEAT_TOL
+        assert rel_err(E.ops.inter_group_bwd(g["r"].to(DEV), idx, 48, **kw), g["dfeats"]) < FEAT_TOL
+    # autograd wrapper with the reference's shadow row appended (p_in + 1 rows, never addressed)
+    f = torch.cat((feats, torch.zeros(1, 3, 1, 60, device=DEV)), 2).requires_grad_(True)
+    out = E.functional.inter_zpconv_grouping_naive(idx, w, f)
+    (out * g["r"].to(DEV)).sum().backward()
+    assert rel_err(out, g["grouped"]) < FEAT_TOL and rel_err(f.grad[:, :, :48], g["dfeats"]) < FEAT_TOL
+    assert float(f.grad[:, :, 48].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("nn_,ks_pts", [(16, 1), (32, 1), (40, 2), (128, 1), (7, 3)])
+def test_inter_group_generic_shapes_vs_oracle(E, O, nn_, ks_pts):
+    from epn_pointcloud_b200 import functional as L
+    b, c, p_in, p = 2, 5, 80, 40
+    xyz = sphere(b, p_in, 400 + nn_)
+    centers = xyz[:, :, :p].contiguous()
+    anchors = torch.from_numpy(L.get_anchors(60))
+    kernels = torch.from_numpy(L.get_sphereical_kernel_points_from_ply(0.35, ks_pts))
+    idx = O.ball_query(centers, xyz, 0.7, nn_)
+    feats = torch.randn(b, c, p_in, 60, generator=torch.Generator().manual_seed(1))
+    w = O.inter_weights(xyz, centers, idx, anchors, kernels, 0.12)
+    want = O.inter_group_fwd(idx, w, feats)
+    geom = tuple(cuda(xyz, centers, anchors, kernels)) + (0.12,)
+    got = E.ops.inter_group_fwd(feats.to(DEV), idx.to(DEV), geom=geom)
+    assert rel_err(got, want) < FEAT_TOL
+    dout = torch.randn(want.shape, generator=torch.Generator().manual_seed(2))
+    assert rel_err(E.ops.inter_group_bwd(dout.to(DEV), idx.to(DEV), p_in, geom=geom),
+                   O.inter_group_bwd(idx, w, dout, p_in)) < FEAT_TOL
+
+
+def test_intra_grouping_vs_golden(E):
+    g = load_golden("intra_group")
+    ii = load_golden("so3_constants")["intra_idx"].int().to(DEV)
+    assert torch.equal(E.ops.intra_group_fwd(g["feats"].to(DEV), ii).cpu(), g["grouped"])
+    assert rel_err(E.ops.intra_group_bwd(g["r"].to(DEV), ii), g["dfeats"]) < 1e-6
+    f = g["feats"].to(DEV).requires_grad_(True)
+    out = E.functional.intra_so3conv_grouping(ii, f)
+    (out * g["r"].to(DEV)).sum().backward()
+    assert rel_err(f.grad, g["dfeats"]) < 1e-6
+
+
+# ------------------------------------------------------------------ conv layers
+def test_basic_conv_vs_golden(E):
+    g = load_golden("basic_conv")
+    conv = E.BasicSO3Conv(3, 5, 24).to(DEV)
+    conv.load_state_dict(g.state_dict())
+    x = g["x"].to(DEV).requires_grad_(True)
+    out = conv(x)
+    (out * g["r"].to(DEV)).sum().backward()
+    assert rel_err(out, g["out"]) < FEAT_TOL
+    assert rel_err(x.grad, g["dx"]) < FEAT_TOL and rel_err(conv.W.grad, g["dW"]) < FEAT_TOL
+
+
+def test_inter_so3conv_occupancy_20_anchors_vs_golden(E):
+    """BASELINE config 1: one 256-pt cloud, 20 anchors, real FPS, occupancy features."""
+    from epn_pointcloud_b200.blocks import preprocess_input
+    g = load_golden("inter_a20_occupancy")
+    conv = E.InterSO3Conv(1, 8, 1, 2, 0.4, 0.08, 16, lazy_sample=False, kanchor=20).to(DEV)
+    conv.load_state_dict(g.state_dict())
+    x = preprocess_input(g["pc"].to(DEV), 20, False)
+    inter_idx, inter_w, sample_idx, y = conv(x)
+    assert torch.equal(sample_idx.cpu(), g["sample_idx"]) and torch.equal(inter_idx.cpu(), g["inter_idx"])
+    assert torch.equal(y.xyz.cpu(), g["new_xyz"])
+    assert rel_err(inter_w.materialize()[:, :8], g["inter_w_p0_8"]) < 1e-5
+    assert rel_err(y.feats, g["out"]) < FEAT_TOL
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    assert rel_err(conv.basic_conv.W.grad, g["dW"]) < FEAT_TOL
+
+
+@pytest.mark.parametrize("name,stride,nn_", [("inter_a60_s1", 1, 16), ("inter_a60_s2", 2, 32)])
+def test_inter_so3conv_60_anchors_vs_golden(E, name, stride, nn_):
+    g = load_golden(name)
+    conv = E.InterSO3Conv(4, 8, 1, stride, 0.6, 0.18, nn_, lazy_sample=True, kanchor=60).to(DEV)
+    conv.load_state_dict(g.state_dict())
+    feats = g["feats"].to(DEV).requires_grad_(True)
+    x = E.SphericalPointCloud(g["pc"].permute(0, 2, 1).contiguous().to(DEV), feats, None)
+    inter_idx, inter_w, sample_idx, y = conv(x)
+    assert torch.equal(inter_idx.cpu(), g["inter_idx"]) and torch.equal(sample_idx.cpu(), g["sample_idx"])
+    assert rel_err(inter_w.materialize()[:, :2], g["inter_w_p0_2"]) < 1e-5
+    assert rel_err(y.feats, g["out"]) < FEAT_TOL
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    assert rel_err(feats.grad, g["dfeats"]) < FEAT_TOL and rel_err(conv.basic_conv.W.grad, g["dW"]) < FEAT_TOL
+    # pass-through of (inter_idx, inter_w) into a second call (base_so3conv.py:148-156 semantics)
+    if stride == 1:
+        i2, w2, s2, y2 = conv(E.SphericalPointCloud(x.xyz, feats.detach(), None), inter_idx, inter_w)
+        assert s2 is None and rel_err(y2.feats, g["out"]) < FEAT_TOL
+        i3, w3, s3, y3 = conv(E.SphericalPointCloud(x.xyz, feats.detach(), None), inter_idx, inter_w.materialize())
+        assert rel_err(y3.feats, g["out"]) < FEAT_TOL
+
+
+def test_intra_so3conv_vs_golden(E):
+    g = load_golden("intra_a60")
+    conv = E.IntraSO3Conv(4, 8).to(DEV)
+    conv.load_state_dict(g.state_dict())
+    feats = g["feats"].to(DEV).requires_grad_(True)
+    y = conv(E.SphericalPointCloud(torch.zeros(2, 3, 32, device=DEV), feats, None))
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    assert rel_err(y.feats, g["out"]) < FEAT_TOL
+    assert rel_err(feats.grad, g["dfeats"]) < FEAT_TOL and rel_err(conv.basic_conv.W.grad, g["dW"]) < FEAT_TOL
+
+
+def test_separable_block_vs_golden(E):
+    from epn_pointcloud_b200.blocks import SeparableSO3ConvBlock
+    g = load_golden("separable_block")
+    blk = SeparableSO3ConvBlock(dict(g["args"])).to(DEV).train()
+    blk.load_state_dict(g.state_dict())
+    feats = g["feats"].to(DEV).requires_grad_(True)
+    x = E.SphericalPointCloud(g["pc"].permute(0, 2, 1).contiguous().to(DEV), feats, None)
+    _, _, _, y = blk(x, None, None)
+    assert rel_err(y.feats, g["out"]) < FEAT_TOL
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    assert rel_err(feats.grad, g["dfeats"]) < 1e-3   # through two batch/instance norms: conditioning, not kernels
+    for k, v in g.grads().items():
+        got = dict(blk.named_parameters())[k].grad
+        if v.abs().max() > 1e-3 * g["dfeats"].abs().max():
+            assert rel_err(got, v) < 2e-3, k
+
+
+def test_backbone_small_vs_golden(E):
+    from epn_pointcloud_b200.blocks import SO3ConvBackbone
+    g = load_golden("backbone_small")
+    model = SO3ConvBackbone(g["params"], 60).to(DEV).train()
+    model.load_state_dict(g.state_dict(), strict=True)
+    y = model(g["pc"].to(DEV))
+    assert torch.equal(y.xyz.cpu(), g["out_xyz"])
+    assert rel_err(y.feats, g["out"]) < 5e-4        # 3 layers deep, 9 normalisations
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    grads = g.grads()
+    k = "backbone.1.blocks.0.intra_conv.conv.basic_conv.W"
+    assert rel_err(dict(model.named_parameters())[k].grad, grads[k]) < 5e-3
+
+
+# ------------------------------------- BASELINE-size cases: oracle-free properties
+def _layer(E, c_in, c_out, stride, nn_, radius, sigma, lazy=True):
+    torch.manual_seed(0)
+    return E.InterSO3Conv(c_in, c_out, 1, stride, radius, sigma, nn_, lazy_sample=lazy, kanchor=60).to(DEV)
+
+
+def test_full_size_fused_equals_unfused_composition(E):
+    """cls layer b0l1 (64->64, P=512, K=16, A=60): fused conv == grouping op + BasicSO3Conv op, and is linear."""
+    conv = _layer(E, 64, 64, 1, 16, 0.2828, 0.04)
+    xyz = sphere(2, 512, 7).to(DEV)
+    f1 = torch.randn(2, 64, 512, 60, device=DEV)
+    f2 = torch.randn(2, 64, 512, 60, device=DEV)
+    idx, w, _, y1 = conv(E.SphericalPointCloud(xyz, f1, None))
+    grouped = E.ops.inter_group_fwd(f1, idx, inter_w=w.materialize())
+    assert rel_err(E.ops.basic_conv_fwd(grouped, conv.basic_conv.W.detach()), y1.feats) < FEAT_TOL
+    _, _, _, y2 = conv(E.SphericalPointCloud(xyz, f2, None))
+    _, _, _, y12 = conv(E.SphericalPointCloud(xyz, 2.0 * f1 - 0.5 * f2, None))
+    assert rel_err(y12.feats, 2.0 * y1.feats - 0.5 * y2.feats) < FEAT_TOL
+
+
+def test_full_size_layer0_anchor_equivariance(E):
+    """Rotating the cloud by an anchor rotation permutes the anchor axis of the output
+    (SURVEY.md section 4): out'[..., a] = out[..., index_of(R_g^T R_a)].  N=1024, K=32, FPS."""
+    from epn_pointcloud_b200.blocks import preprocess_input
+    conv = _layer(E, 1, 64, 2, 32, 0.2, 0.02, lazy=False)
+    R = conv.anchors.double().cpu()
+    pc = sphere(2, 1024, 9).permute(0, 2, 1).contiguous()
+    gi = 17
+    pc_rot = (pc.double() @ R[gi].T).float()
+    i1, _, s1, y1 = conv(preprocess_input(pc.to(DEV), 60, False))
+    i2, _, s2, y2 = conv(preprocess_input(pc_rot.to(DEV), 60, False))
+    if not (torch.equal(i1, i2) and torch.equal(s1, s2)):
+        pytest.skip("rounding moved a point across the ball/FPS boundary under rotation")
+    perm = [int((R - (R[gi].T @ R[a])).abs().amax(dim=(1, 2)).argmin()) for a in range(60)]
+    assert rel_err(y2.feats, y1.feats[..., perm]) < 1e-3  # rotated inputs are rounded to fp32: geometric noise
+
+
+def test_full_size_intra_matches_permutation_identity(E):
+    """IntraSO3Conv with W = one-hot on kernel slot k copies anchor intra_idx[a,k]: exact."""
+    conv = E.IntraSO3Conv(64, 64).to(DEV)
+    ii = conv.intra_idx
+    feats = torch.randn(4, 64, 512, 60, device=DEV)
+    for k in (0, 5, 11):
+        W = torch.zeros(64, 64, 12, device=DEV)
+        W[torch.arange(64), torch.arange(64), k] = 1.0
+        with torch.no_grad():
+            conv.basic_conv.W.copy_(W.view(64, 768))
+        y = conv(E.SphericalPointCloud(None, feats, None)).feats
+        assert rel_err(y, feats[..., ii[:, k]]) < 1e-6
+
+
+def test_full_size_gradcheck_by_adjoint_identity(E):
+    """<conv(f), r> differentiated w.r.t. f equals conv^T r: check <conv(f), r> == <f, dfeats> (linearity)
+    and the same for W, at cls layer b1l0 size (64->128, 512->256, K=32)."""
+    conv = _layer(E, 64, 128, 2, 32, 0.4, 0.08)
+    xyz = sphere(2, 512, 11).to(DEV)
+    f = torch.randn(2, 64, 512, 60, device=DEV, requires_grad=True)
+    _, _, _, y = conv(E.SphericalPointCloud(xyz, f, None))
+    r = torch.randn_like(y.feats)
+    s = (y.feats * r).sum()
+    s.backward()
+    lhs = float(s)
+    assert abs(float((f.detach() * f.grad).sum()) - lhs) <= 2e-4 * abs(lhs) + 1e-2
+    assert abs(float((conv.basic_conv.W.detach() * conv.basic_conv.W.grad).sum()) - lhs) <= 2e-4 * abs(lhs) + 1e-2
+
+
+def test_error_behaviour_on_device(E):
+    from epn_pointcloud_b200 import _lib
+    L = _lib.lib()
+    x = torch.zeros(1, 3, 8, device=DEV)
+    with pytest.raises(RuntimeError):
+        E.ops.ball_query(x.permute(0, 2, 1), x, 0.1, 4)  # non-contiguous
+    rc = L.epn_inter_so3conv_fwd_f32(None, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 0.1,
+                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, 1, 1, 4, 8, 8, 4, 60, 24, None)
+    assert rc == -3 and b"workspace" in L.epn_last_error()
