@@ -30,7 +30,7 @@ import torch  # noqa: E402
 
 METRIC = "point-clouds/sec, ModelNet40 1024-pt 60-anchor SPConv fwd+bwd"
 N_POINTS, N_ANCHORS, KS, KN = 1024, 60, 24, 12
-CLASSES = ["index_ops", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group", "channel_gemm", "other"]
+CLASSES = ["index_ops", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group", "channel_gemm", "split_convert"]
 
 
 def synthetic_clouds(b, n, seed):
@@ -171,6 +171,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU per step (weak scaling)")
     ap.add_argument("--ref-batch", type=int, default=2, help="clouds per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run warm-up, then ONE step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -227,6 +229,14 @@ def main():
 
     for _ in range(args.warmup):
         step(x_dev)
+    if args.profile_step:
+        # for `ncu --profile-from-start off ...`: exactly one step inside the profiler range, no timing
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(x_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- device-resident timing ("value")
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -75,8 +75,13 @@ SIGNATURES = {
     "epn_intra_so3conv_workspace_bytes": (c_sz, [c_i] * 7),
     "epn_intra_so3conv_fwd_f32": (c_i, [c_f] * 5 + [c_sz] + [c_i] * 6 + [c_f]),
     "epn_intra_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_sz] + [c_i] * 6 + [c_f]),
-    "epn_basic_conv_fwd_f32": (c_i, [c_f] * 3 + [c_i] * 4 + [c_f]),
-    "epn_basic_conv_bwd_f32": (c_i, [c_f] * 5 + [c_i] * 4 + [c_f]),
+    "epn_basic_conv_workspace_bytes": (c_sz, [c_i] * 4),
+    "epn_basic_conv_fwd_f32": (c_i, [c_f] * 4 + [c_sz] + [c_i] * 4 + [c_f]),
+    "epn_basic_conv_bwd_f32": (c_i, [c_f] * 6 + [c_sz] + [c_i] * 4 + [c_f]),
+    "epn_set_gemm_backend": (None, [c_i]),
+    "epn_set_slab_bytes": (None, [c_sz]),
+    "epn_get_slab_bytes": (c_sz, []),
+    "epn_get_gemm_backend": (c_i, []),
 }
 
 _lib = None

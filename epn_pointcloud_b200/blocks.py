@@ -102,7 +102,10 @@ class SeparableSO3ConvBlock(nn.Module):
             x = self.intra_conv(x)
         if self.stride > 1:
             skip_feature = L.batched_index_select(skip_feature, 2, sample_idx.long())
-        skip_feature = self.skip_conv(skip_feature)
+        # 1x1 skip conv = a BasicSO3Conv with kernel size 1: run it through the library's fp32-faithful
+        # channel GEMM (cuDNN would silently use TF32), parameters stay in nn.Conv2d for checkpoint parity
+        w = self.skip_conv.weight.view(self.skip_conv.out_channels, self.skip_conv.in_channels)
+        skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w) + self.skip_conv.bias.view(1, -1, 1, 1)
         skip_feature = self.relu(self.norm(skip_feature))
         x_out = sptk.SphericalPointCloud(x.xyz, x.feats + skip_feature, x.anchors)
         return inter_idx, inter_w, sample_idx, x_out

@@ -31,6 +31,7 @@ enum KernelClass {
     KC_INTRA_GROUP = 3,  // intra grouping fwd/bwd
     KC_GEMM = 4,         // channel GEMMs (fwd, dX, dW)
     KC_OTHER = 5,
+    KC_SPLIT = 5,        // fp32 -> bf16 hi/lo split-tile conversion passes
     KC_COUNT = 6
 };
 

@@ -4,31 +4,52 @@
 //   IntraSO3Conv  = anchor-permutation gather + channel GEMM   (modules.py:197-200)
 //   BasicSO3Conv  = channel GEMM on an already grouped tensor  (modules.py:48-55)
 //
-// Schedule: the batch is cut into slabs of (clouds x point range) whose grouped
-// tensor G[c*ks, points*na] fits the L2 (EPN_SLAB_BYTES); the grouping kernel
-// writes the slab, the GEMM consumes it while it is still L2-resident, so
-// neither inter_w nor the gathered (B,C,P,K,A) tensor nor the full grouped
-// tensor ever reaches HBM.  The workspace is one slab (+ weight staging).
+// Schedule: the batch is cut into slabs of (clouds x point range) whose grouped tensor
+// G[c*ks, clouds*points*na] fits the L2 (EPN_SLAB_BYTES); the grouping kernel writes the slab, a
+// conversion pass turns it into bf16 hi/lo split tiles, and the tcgen05 GEMM consumes them while
+// they are L2-resident, so neither inter_w nor the gathered (B,C,P,K,A) tensor nor the full
+// grouped tensor ever reaches HBM.  The workspace holds one slab + its operand tiles.
+// EPN_GEMM=simt (or epn_set_gemm_backend(1)) routes the same schedule through the fp32 SIMT GEMM
+// (cross-check path of the GPU tests).
 #include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
 
 #include "epn_internal.cuh"
 
 namespace epn {
 
-static size_t slab_budget_bytes() {
-    static size_t v = 0;
-    if (v == 0) {
-        const char *e = getenv("EPN_SLAB_BYTES");
-        v = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)48 << 20;
-        if (v < ((size_t)1 << 20)) v = (size_t)1 << 20;
+static std::atomic<int> g_backend{-1};  // 0 = tcgen05, 1 = SIMT
+
+static int gemm_backend() {
+    int v = g_backend.load();
+    if (v < 0) {
+        const char *e = getenv("EPN_GEMM");
+        v = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+        g_backend.store(v);
     }
     return v;
 }
 
+static std::atomic<size_t> g_slab_bytes{0};
+
+static size_t slab_budget_bytes() {
+    size_t v = g_slab_bytes.load();
+    if (v == 0) {
+        const char *e = getenv("EPN_SLAB_BYTES");
+        v = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)32 << 20;
+        if (v < ((size_t)64 << 10)) v = (size_t)64 << 10;
+        g_slab_bytes.store(v);
+    }
+    return v;
+}
+
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 struct SlabPlan {
     int bc;  // clouds per slab
     int pc;  // points per slab (pc == p when bc > 1)
-    size_t bytes;
 };
 
 static SlabPlan plan_slabs(int b, int ck, int p, int na) {
@@ -46,18 +67,124 @@ static SlabPlan plan_slabs(int b, int ck, int p, int na) {
         if (s.pc < 1) s.pc = 1;
         if (s.pc > p) s.pc = p;
     }
-    s.bytes = (size_t)s.bc * s.pc * per_point;
     return s;
 }
 
-static int pick_split_k(int M, int N, int K, int batch) {
-    const long long tiles = (long long)cdiv(M, 64) * cdiv(N, 64) * batch;
-    long long sk = (148LL * 6 + tiles - 1) / tiles;
-    const long long maxk = K / 256 > 0 ? K / 256 : 1;
+// Workspace carve-up shared by the three convs.
+struct Workspace {
+    float *slab;      // fp32 grouped slab  [ck][n_slab]
+    uint8_t *tilesA;  // 128-row operand tiles (activations)
+    uint8_t *tilesB;  // dout tiles for dW
+    uint8_t *tilesW;  // weights  (rows = c_out, K = ck)
+    uint8_t *tilesWT; // weights^T (rows = ck, K = c_out)
+    size_t total;
+};
+
+static Workspace carve(void *base, int ck, int c_out, long long n_slab, bool need_slab) {
+    Workspace w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        uint8_t *p = base ? static_cast<uint8_t *>(base) + off : nullptr;
+        off += up256(bytes);
+        return p;
+    };
+    w.slab = reinterpret_cast<float *>(take(need_slab ? (size_t)ck * n_slab * sizeof(float) : 0));
+    size_t a = split_tiles_bytes(n_slab, ck, 128);
+    const size_t a2 = split_tiles_bytes(n_slab, c_out, 128), a3 = split_tiles_bytes(ck, n_slab, 128);
+    if (a2 > a) a = a2;
+    if (a3 > a) a = a3;
+    w.tilesA = take(a);
+    w.tilesB = take(split_tiles_bytes(c_out, n_slab, umma_trb_for(c_out)));
+    w.tilesW = take(split_tiles_bytes(c_out, ck, umma_trb_for(c_out)));
+    w.tilesWT = take(split_tiles_bytes(ck, c_out, umma_trb_for(ck)));
+    w.total = off;
+    return w;
+}
+
+// A [rows_k x (bc x cols)] fp32 matrix view: element (k, z, j) = ptr[z*stride_z + k*stride_k + j]
+struct ColsView {
+    float *ptr;
+    long long stride_z, stride_k;
+};
+
+constexpr long long HUGE_Z = 1LL << 60;
+
+static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s) {
+    if (gemm_backend() != 0) return 0;
+    if (fwd) {
+        SplitSrc src{W, HUGE_Z, 0, ck, HUGE_Z, 0, 1};
+        int rc = launch_split_tiles(src, ws.tilesW, c_out, ck, umma_trb_for(c_out), s);
+        if (rc) return rc;
+    }
+    if (transposed) {
+        SplitSrc src{W, HUGE_Z, 0, 1, HUGE_Z, 0, ck};
+        int rc = launch_split_tiles(src, ws.tilesWT, ck, c_out, umma_trb_for(ck), s);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int pick_split_k(int M, int N, long long K, int batch, int tile_m, int tile_n, int k_unit) {
+    const long long tiles = (long long)cdiv(M, tile_m) * cdiv(N, tile_n) * batch;
+    long long sk = (148LL * 4 + tiles - 1) / tiles;
+    const long long maxk = K / k_unit > 0 ? K / k_unit : 1;
     if (sk > maxk) sk = maxk;
     if (sk < 1) sk = 1;
     if (sk * batch > 65535) sk = 65535 / batch;
     return (int)sk;
+}
+
+// out(c_out) = W . in(ck)
+static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long long cols, ColsView out,
+                    const Workspace &ws, cudaStream_t s) {
+    if (gemm_backend() != 0) {
+        GemmOperand A{W, 0, ck, 1};
+        GemmOperand B{in.ptr, in.stride_z, in.stride_k, 1};
+        return launch_sgemm(A, B, out.ptr, out.stride_z, out.stride_k, c_out, (int)cols, ck, bc, 1, 0, s);
+    }
+    const long long n = bc * cols;
+    SplitSrc src{in.ptr, cols, in.stride_z, 1, HUGE_Z, 0, in.stride_k};
+    int rc = launch_split_tiles(src, ws.tilesA, n, ck, 128, s);
+    if (rc) return rc;
+    GemmEpilogue ep{out.ptr, cols, out.stride_z, 1, out.stride_k, false};
+    return launch_umma_gemm(ws.tilesA, ws.tilesW, (int)n, c_out, ck, umma_trb_for(c_out), ep, 1, s);
+}
+
+// din(ck) = W^T . dout(c_out)
+static int gemm_dx(const float *W, int c_out, int ck, ColsView dout, int bc, long long cols, ColsView din,
+                   const Workspace &ws, cudaStream_t s) {
+    if (gemm_backend() != 0) {
+        GemmOperand A{W, 0, 1, ck};
+        GemmOperand B{dout.ptr, dout.stride_z, dout.stride_k, 1};
+        return launch_sgemm(A, B, din.ptr, din.stride_z, din.stride_k, ck, (int)cols, c_out, bc, 1, 0, s);
+    }
+    const long long n = bc * cols;
+    SplitSrc src{dout.ptr, cols, dout.stride_z, 1, HUGE_Z, 0, dout.stride_k};
+    int rc = launch_split_tiles(src, ws.tilesA, n, c_out, 128, s);
+    if (rc) return rc;
+    GemmEpilogue ep{din.ptr, cols, din.stride_z, 1, din.stride_k, false};
+    return launch_umma_gemm(ws.tilesA, ws.tilesWT, (int)n, ck, c_out, umma_trb_for(ck), ep, 1, s);
+}
+
+// dW(c_out x ck) += dout(c_out) . in(ck)^T      (dW pre-zeroed by the caller)
+static int gemm_dw(ColsView dout, ColsView in, int c_out, int ck, int bc, long long cols, float *dW,
+                   const Workspace &ws, cudaStream_t s) {
+    if (gemm_backend() != 0) {
+        GemmOperand A{dout.ptr, dout.stride_z, dout.stride_k, 1};
+        GemmOperand B{in.ptr, in.stride_z, 1, in.stride_k};
+        return launch_sgemm(A, B, dW, 0, ck, c_out, ck, (int)cols, bc, pick_split_k(c_out, ck, cols, bc, 64, 64, 256),
+                            2, s);
+    }
+    const long long n = bc * cols;
+    SplitSrc sa{in.ptr, HUGE_Z, 0, in.stride_k, cols, in.stride_z, 1};
+    int rc = launch_split_tiles(sa, ws.tilesA, ck, n, 128, s);
+    if (rc) return rc;
+    const int trb = umma_trb_for(c_out);
+    SplitSrc sb{dout.ptr, HUGE_Z, 0, dout.stride_k, cols, dout.stride_z, 1};
+    rc = launch_split_tiles(sb, ws.tilesB, c_out, n, trb, s);
+    if (rc) return rc;
+    GemmEpilogue ep{dW, HUGE_Z, 0, 1, ck, true};
+    return launch_umma_gemm(ws.tilesA, ws.tilesB, ck, c_out, n, trb, ep, pick_split_k(ck, c_out, n, 1, 128, trb, 256), s);
 }
 
 }  // namespace epn
@@ -70,34 +197,73 @@ using namespace epn;
         const int rc__ = (expr); \
         if (rc__ != 0) return rc__; \
     } while (0)
+#define EPN_CHECK_WS(need)                                                                                      \
+    do {                                                                                                        \
+        EPN_REQUIRE_PTR(workspace);                                                                             \
+        EPN_REQUIRE(workspace_bytes >= (need), EPN_ERR_WORKSPACE, "workspace smaller than *_workspace_bytes()"); \
+        EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");      \
+    } while (0)
+
+EPN_API void epn_set_slab_bytes(size_t bytes) { g_slab_bytes.store(bytes < ((size_t)64 << 10) ? ((size_t)64 << 10) : bytes); }
+EPN_API size_t epn_get_slab_bytes(void) { return slab_budget_bytes(); }
+EPN_API void epn_set_gemm_backend(int simt) { g_backend.store(simt ? 1 : 0); }
+EPN_API int epn_get_gemm_backend(void) { return gemm_backend(); }
 
 // ------------------------------------------------------------------ BasicSO3Conv
-EPN_API int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, int b, int ck, int co, int pa,
-                                   void *stream) {
+EPN_API size_t epn_basic_conv_workspace_bytes(int b, int ck, int co, int pa) {
+    if (b <= 0 || ck <= 0 || co <= 0 || pa <= 0) return 0;
+    const SlabPlan sp = plan_slabs(b, ck, pa, 1);
+    return carve(nullptr, ck, co, (long long)sp.bc * sp.pc, false).total;
+}
+
+EPN_API int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, void *workspace,
+                                   size_t workspace_bytes, int b, int ck, int co, int pa, void *stream) {
     EPN_REQUIRE_PTR(x); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(ck); EPN_REQUIRE_POS(co); EPN_REQUIRE_POS(pa); EPN_CHECK_B(b);
-    GemmOperand A{W, 0, ck, 1};
-    GemmOperand B{x, (long long)ck * pa, pa, 1};
-    return launch_sgemm(A, B, out, (long long)co * pa, pa, co, pa, ck, b, 1, 0, as_stream(stream));
+    const SlabPlan sp = plan_slabs(b, ck, pa, 1);
+    const Workspace ws = carve(workspace, ck, co, (long long)sp.bc * sp.pc, false);
+    EPN_CHECK_WS(ws.total);
+    cudaStream_t s = as_stream(stream);
+    EPN_TRY(prep_weights(W, co, ck, ws, true, false, s));
+    for (int b0 = 0; b0 < b; b0 += sp.bc) {
+        const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
+        for (int j0 = 0; j0 < pa; j0 += sp.pc) {
+            const long long cols = pa - j0 < sp.pc ? pa - j0 : sp.pc;
+            ColsView in{const_cast<float *>(x) + (size_t)b0 * ck * pa + j0, (long long)ck * pa, pa};
+            ColsView o{out + (size_t)b0 * co * pa + j0, (long long)co * pa, pa};
+            EPN_TRY(gemm_fwd(W, co, ck, in, bc, cols, o, ws, s));
+        }
+    }
+    return 0;
 }
 
 EPN_API int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, float *dx, float *dW,
-                                   int b, int ck, int co, int pa, void *stream) {
+                                   void *workspace, size_t workspace_bytes, int b, int ck, int co, int pa,
+                                   void *stream) {
     EPN_REQUIRE_PTR(dout);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(ck); EPN_REQUIRE_POS(co); EPN_REQUIRE_POS(pa); EPN_CHECK_B(b);
+    if (dx != nullptr) EPN_REQUIRE_PTR(W);
+    if (dW != nullptr) EPN_REQUIRE_PTR(x);
+    const SlabPlan sp = plan_slabs(b, ck, pa, 1);
+    const Workspace ws = carve(workspace, ck, co, (long long)sp.bc * sp.pc, false);
+    EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    if (dx != nullptr) {
-        EPN_REQUIRE_PTR(W);
-        GemmOperand A{W, 0, 1, ck};  // W^T: (m=ck index, k=co index)
-        GemmOperand B{dout, (long long)co * pa, pa, 1};
-        EPN_TRY(launch_sgemm(A, B, dx, (long long)ck * pa, pa, ck, pa, co, b, 1, 0, s));
-    }
-    if (dW != nullptr) {
-        EPN_REQUIRE_PTR(x);
-        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)co * ck, s);
-        GemmOperand A{dout, (long long)co * pa, pa, 1};
-        GemmOperand B{x, (long long)ck * pa, 1, pa};  // x^T: (k=pa index, n=ck index)
-        EPN_TRY(launch_sgemm(A, B, dW, 0, ck, co, ck, pa, b, pick_split_k(co, ck, pa, b), 2, s));
+    if (dx != nullptr) EPN_TRY(prep_weights(W, co, ck, ws, false, true, s));
+    if (dW != nullptr) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)co * ck, s);
+    for (int b0 = 0; b0 < b; b0 += sp.bc) {
+        const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
+        for (int j0 = 0; j0 < pa; j0 += sp.pc) {
+            const long long cols = pa - j0 < sp.pc ? pa - j0 : sp.pc;
+            ColsView d{const_cast<float *>(dout) + (size_t)b0 * co * pa + j0, (long long)co * pa, pa};
+            if (dx != nullptr) {
+                ColsView di{dx + (size_t)b0 * ck * pa + j0, (long long)ck * pa, pa};
+                EPN_TRY(gemm_dx(W, co, ck, d, bc, cols, di, ws, s));
+            }
+            if (dW != nullptr) {
+                ColsView in{const_cast<float *>(x) + (size_t)b0 * ck * pa + j0, (long long)ck * pa, pa};
+                EPN_TRY(gemm_dw(d, in, co, ck, bc, cols, dW, ws, s));
+            }
+        }
     }
     return 0;
 }
@@ -105,9 +271,10 @@ EPN_API int epn_basic_conv_bwd_f32(const float *dout, const float *x, const floa
 // ------------------------------------------------------------------ InterSO3Conv
 EPN_API size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int p_in, int p, int nn, int na,
                                                  int ks, int backward) {
-    (void)c_out; (void)p_in; (void)nn; (void)backward;
-    if (b <= 0 || c_in <= 0 || p <= 0 || na <= 0 || ks <= 0) return 0;
-    return plan_slabs(b, c_in * ks, p, na).bytes;
+    (void)p_in; (void)nn; (void)backward;
+    if (b <= 0 || c_in <= 0 || c_out <= 0 || p <= 0 || na <= 0 || ks <= 0) return 0;
+    const SlabPlan sp = plan_slabs(b, c_in * ks, p, na);
+    return carve(nullptr, c_in * ks, c_out, (long long)sp.bc * sp.pc * na, true).total;
 }
 
 EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
@@ -116,7 +283,7 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
                                       size_t workspace_bytes, int b, int c_in, int c_out, int p_in, int p,
                                       int nn, int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx); EPN_REQUIRE_PTR(anchors);
-    EPN_REQUIRE_PTR(kernels); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out); EPN_REQUIRE_PTR(workspace);
+    EPN_REQUIRE_PTR(kernels); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
     EPN_REQUIRE_POS(nn); EPN_REQUIRE_POS(na); EPN_REQUIRE_POS(ks); EPN_CHECK_B(b);
     EPN_REQUIRE(na <= 64, EPN_ERR_SHAPE, "na > 64 anchors not supported");
@@ -124,23 +291,22 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     EPN_REQUIRE(feats != nullptr || c_in == 1, EPN_ERR_NULL, "feats NULL requires c_in == 1");
     const int ck = c_in * ks;
     const SlabPlan sp = plan_slabs(b, ck, p, na);
-    EPN_REQUIRE(workspace_bytes >= sp.bytes, EPN_ERR_WORKSPACE, "workspace smaller than epn_inter_so3conv_workspace_bytes()");
-    EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");
+    const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
+    EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    float *G = static_cast<float *>(workspace);
+    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int p0 = 0; p0 < p; p0 += sp.pc) {
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
-            const long long cols = (long long)pc * na;
+            const long long cols = (long long)pc * na, n_slab = bc * cols;
             InterGeom g{xyz + (size_t)b0 * 3 * p_in, centers + (size_t)b0 * 3 * p, anchors, kernels, sigma};
             EPN_TRY(launch_inter_group_fwd(feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr,
-                                           idx + (size_t)b0 * p * nn, nullptr, g, G, (long long)ck * cols, cols, p0, pc,
-                                           bc, c_in, p_in, p, nn, na, ks, s));
-            GemmOperand A{W, 0, ck, 1};
-            GemmOperand B{G, (long long)ck * cols, cols, 1};
-            EPN_TRY(launch_sgemm(A, B, out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na,
-                                 (long long)p * na, c_out, (int)cols, ck, bc, 1, 0, s));
+                                           idx + (size_t)b0 * p * nn, nullptr, g, ws.slab, cols, n_slab, p0, pc, bc,
+                                           c_in, p_in, p, nn, na, ks, s));
+            ColsView in{ws.slab, cols, n_slab};
+            ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
+            EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
         }
     }
     return 0;
@@ -152,7 +318,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
                                       float *dW, void *workspace, size_t workspace_bytes, int b, int c_in,
                                       int c_out, int p_in, int p, int nn, int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx);
-    EPN_REQUIRE_PTR(anchors); EPN_REQUIRE_PTR(kernels); EPN_REQUIRE_PTR(workspace);
+    EPN_REQUIRE_PTR(anchors); EPN_REQUIRE_PTR(kernels);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
     EPN_REQUIRE_POS(nn); EPN_REQUIRE_POS(na); EPN_REQUIRE_POS(ks); EPN_CHECK_B(b);
     EPN_REQUIRE(na <= 64, EPN_ERR_SHAPE, "na > 64 anchors not supported");
@@ -161,36 +327,35 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     if (dfeats != nullptr) EPN_REQUIRE_PTR(W);
     const int ck = c_in * ks;
     const SlabPlan sp = plan_slabs(b, ck, p, na);
-    EPN_REQUIRE(workspace_bytes >= sp.bytes, EPN_ERR_WORKSPACE, "workspace smaller than epn_inter_so3conv_workspace_bytes()");
-    EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");
+    const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
+    EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    float *G = static_cast<float *>(workspace);
-    if (dfeats != nullptr) cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)b * c_in * p_in * na, s);
+    if (dfeats != nullptr) {
+        cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)b * c_in * p_in * na, s);
+        EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));
+    }
     if (dW != nullptr) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)c_out * ck, s);
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int p0 = 0; p0 < p; p0 += sp.pc) {
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
-            const long long cols = (long long)pc * na;
+            const long long cols = (long long)pc * na, n_slab = bc * cols;
             InterGeom g{xyz + (size_t)b0 * 3 * p_in, centers + (size_t)b0 * 3 * p, anchors, kernels, sigma};
-            const float *dout_slab = dout + ((size_t)b0 * c_out * p + p0) * na;
+            ColsView d{const_cast<float *>(dout) + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na,
+                       (long long)p * na};
+            ColsView slab{ws.slab, cols, n_slab};
             const int32_t *idx_b = idx + (size_t)b0 * p * nn;
             if (dfeats != nullptr) {
-                // dG = W^T . dout_slab, then scatter through the transposed spatial contraction
-                GemmOperand A{W, 0, 1, ck};
-                GemmOperand B{dout_slab, (long long)c_out * p * na, (long long)p * na, 1};
-                EPN_TRY(launch_sgemm(A, B, G, (long long)ck * cols, cols, ck, (int)cols, c_out, bc, 1, 0, s));
-                EPN_TRY(launch_inter_group_bwd(G, (long long)ck * cols, cols, p0, pc, idx_b, nullptr, g,
+                // dG = W^T . dout, then scatter through the transposed spatial contraction
+                EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
+                EPN_TRY(launch_inter_group_bwd(ws.slab, cols, n_slab, p0, pc, idx_b, nullptr, g,
                                                dfeats + (size_t)b0 * c_in * p_in * na, bc, c_in, p_in, p, nn, na, ks, s));
             }
             if (dW != nullptr) {
-                // dW += dout_slab . G^T with G recomputed (never saved by the forward)
+                // dW += dout . G^T with G recomputed (never saved by the forward)
                 EPN_TRY(launch_inter_group_fwd(feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr, idx_b, nullptr,
-                                               g, G, (long long)ck * cols, cols, p0, pc, bc, c_in, p_in, p, nn, na, ks, s));
-                GemmOperand A{dout_slab, (long long)c_out * p * na, (long long)p * na, 1};
-                GemmOperand B{G, (long long)ck * cols, 1, cols};
-                EPN_TRY(launch_sgemm(A, B, dW, 0, ck, c_out, ck, (int)cols, bc,
-                                     pick_split_k(c_out, ck, (int)cols, bc), 2, s));
+                                               g, ws.slab, cols, n_slab, p0, pc, bc, c_in, p_in, p, nn, na, ks, s));
+                EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
             }
         }
     }
@@ -200,35 +365,34 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
 // ------------------------------------------------------------------ IntraSO3Conv
 EPN_API size_t epn_intra_so3conv_workspace_bytes(int b, int c_in, int c_out, int p, int na, int kn,
                                                  int backward) {
-    (void)c_out; (void)backward;
-    if (b <= 0 || c_in <= 0 || p <= 0 || na <= 0 || kn <= 0) return 0;
-    return plan_slabs(b, c_in * kn, p, na).bytes;
+    (void)backward;
+    if (b <= 0 || c_in <= 0 || c_out <= 0 || p <= 0 || na <= 0 || kn <= 0) return 0;
+    const SlabPlan sp = plan_slabs(b, c_in * kn, p, na);
+    return carve(nullptr, c_in * kn, c_out, (long long)sp.bc * sp.pc * na, true).total;
 }
 
 EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
                                       void *workspace, size_t workspace_bytes, int b, int c_in, int c_out,
                                       int p, int na, int kn, void *stream) {
     EPN_REQUIRE_PTR(feats); EPN_REQUIRE_PTR(intra_idx); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
-    EPN_REQUIRE_PTR(workspace);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
     const int ck = c_in * kn;
     const SlabPlan sp = plan_slabs(b, ck, p, na);
-    EPN_REQUIRE(workspace_bytes >= sp.bytes, EPN_ERR_WORKSPACE, "workspace smaller than epn_intra_so3conv_workspace_bytes()");
-    EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");
+    const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
+    EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    float *G = static_cast<float *>(workspace);
+    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int p0 = 0; p0 < p; p0 += sp.pc) {
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
-            const long long cols = (long long)pc * na;
-            EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, G, (long long)ck * cols, cols,
-                                           p0, pc, bc, c_in, p, na, kn, s));
-            GemmOperand A{W, 0, ck, 1};
-            GemmOperand B{G, (long long)ck * cols, cols, 1};
-            EPN_TRY(launch_sgemm(A, B, out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na,
-                                 (long long)p * na, c_out, (int)cols, ck, bc, 1, 0, s));
+            const long long cols = (long long)pc * na, n_slab = bc * cols;
+            EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0, pc,
+                                           bc, c_in, p, na, kn, s));
+            ColsView in{ws.slab, cols, n_slab};
+            ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
+            EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
         }
     }
     return 0;
@@ -238,38 +402,35 @@ EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, con
                                       const float *W, float *dfeats, float *dW, void *workspace,
                                       size_t workspace_bytes, int b, int c_in, int c_out, int p, int na, int kn,
                                       void *stream) {
-    EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(intra_idx); EPN_REQUIRE_PTR(workspace);
+    EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(intra_idx);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
     if (dfeats != nullptr) EPN_REQUIRE_PTR(W);
     if (dW != nullptr) EPN_REQUIRE_PTR(feats);
     const int ck = c_in * kn;
     const SlabPlan sp = plan_slabs(b, ck, p, na);
-    EPN_REQUIRE(workspace_bytes >= sp.bytes, EPN_ERR_WORKSPACE, "workspace smaller than epn_intra_so3conv_workspace_bytes()");
-    EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");
+    const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
+    EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    float *G = static_cast<float *>(workspace);
+    if (dfeats != nullptr) EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));
     if (dW != nullptr) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)c_out * ck, s);
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int p0 = 0; p0 < p; p0 += sp.pc) {
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
-            const long long cols = (long long)pc * na;
-            const float *dout_slab = dout + ((size_t)b0 * c_out * p + p0) * na;
+            const long long cols = (long long)pc * na, n_slab = bc * cols;
+            ColsView d{const_cast<float *>(dout) + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na,
+                       (long long)p * na};
+            ColsView slab{ws.slab, cols, n_slab};
             if (dfeats != nullptr) {
-                GemmOperand A{W, 0, 1, ck};
-                GemmOperand B{dout_slab, (long long)c_out * p * na, (long long)p * na, 1};
-                EPN_TRY(launch_sgemm(A, B, G, (long long)ck * cols, cols, ck, (int)cols, c_out, bc, 1, 0, s));
-                EPN_TRY(launch_intra_group_bwd(G, (long long)ck * cols, cols, p0, pc, intra_idx,
+                EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
+                EPN_TRY(launch_intra_group_bwd(ws.slab, cols, n_slab, p0, pc, intra_idx,
                                                dfeats + (size_t)b0 * c_in * p * na, bc, c_in, p, na, kn, s));
             }
             if (dW != nullptr) {
-                EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, G, (long long)ck * cols,
-                                               cols, p0, pc, bc, c_in, p, na, kn, s));
-                GemmOperand A{dout_slab, (long long)c_out * p * na, (long long)p * na, 1};
-                GemmOperand B{G, (long long)ck * cols, 1, cols};
-                EPN_TRY(launch_sgemm(A, B, dW, 0, ck, c_out, ck, (int)cols, bc,
-                                     pick_split_k(c_out, ck, (int)cols, bc), 2, s));
+                EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0,
+                                               pc, bc, c_in, p, na, kn, s));
+                EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
             }
         }
     }

@@ -1,0 +1,227 @@
+// Tensor-core channel GEMM of the SPConv path on tcgen05 (sm_100a):
+//     D[128-row tile, N] (+)= sum_kb  A_tile(rt, kb) * B_tile(nt, kb)^T
+// Both operands are "split tiles" (bf16 hi/lo, canonical K-major no-swizzle layout, see
+// epn_umma.cuh) living in global memory / L2; a stage is moved with two cp.async.bulk
+// (UBLKCP) copies that complete on an mbarrier, three tcgen05.mma (hi*hi, hi*lo, lo*hi) per
+// 16-wide k step accumulate in fp32 in TMEM, and four epilogue warps read the accumulator with
+// tcgen05.ld and write rows (= point/anchor columns of the conv) with coalesced stores or REDs.
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 bulk-copy
+// producer (one elected lane), warp 5 TMEM allocator + MMA issuer (one elected lane).
+#include "epn_internal.cuh"
+#include "epn_umma.cuh"
+
+namespace epn {
+using namespace umma;
+
+// ------------------------------------------------------------------ fp32 -> split tiles
+// thread <-> (row, 8-wide k chunk); lanes run along rows so the 16-byte tile stores of a warp are
+// contiguous; source reads are coalesced when rows are contiguous in memory and whole 32-byte
+// sectors per lane when k is contiguous.
+__global__ void __launch_bounds__(256)
+split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int row_tiles, int k_blocks) {
+    const long long rows_pad = (long long)row_tiles * tr;
+    const long long total = rows_pad * k_blocks * (KB / 8);
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t % rows_pad;
+        const int kcg = (int)(t / rows_pad);
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        if (row < rows) {
+            const float *base = src.ptr + (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const long long k = (long long)kcg * 8 + i;
+                if (k < K) x[i] = __ldg(base + (k / src.k_per_z) * src.stride_kz + (k % src.k_per_z) * src.stride_k);
+            }
+        }
+        uint4 hi, lo;
+        split8(x, hi, lo);
+        const int rt = (int)(row / tr), r = (int)(row % tr), kb = kcg / (KB / 8), kc = kcg % (KB / 8);
+        uint8_t *tile = dst + ((size_t)rt * k_blocks + kb) * tile_bytes(tr);
+        *reinterpret_cast<uint4 *>(tile + (size_t)kc * tr * 16 + (size_t)r * 16) = hi;
+        *reinterpret_cast<uint4 *>(tile + part_bytes(tr) + (size_t)kc * tr * 16 + (size_t)r * 16) = lo;
+    }
+}
+
+size_t split_tiles_bytes(long long rows, long long K, int tr) {
+    const long long row_tiles = (rows + tr - 1) / tr, k_blocks = (K + KB - 1) / KB;
+    return (size_t)row_tiles * k_blocks * tile_bytes(tr);
+}
+
+int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s) {
+    const int row_tiles = (int)((rows + tr - 1) / tr), k_blocks = (int)((K + KB - 1) / KB);
+    const long long total = (long long)row_tiles * tr * k_blocks * (KB / 8);
+    long long grid = (total + 255) / 256;
+    if (grid > 148LL * 64) grid = 148LL * 64;
+    ProfScope prof(s, KC_SPLIT);
+    split_tiles_kernel<<<(int)grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
+                                                  k_blocks);
+    return check_launch("split_tiles_kernel");
+}
+
+// ------------------------------------------------------------------ GEMM
+struct UmmaGemmParams {
+    const uint8_t *A;  // [m_tiles][k_blocks] tiles of 128 rows
+    const uint8_t *B;  // [n_tiles][k_blocks] tiles of trb rows
+    int k_blocks, trb, stages;
+    uint32_t tmem_cols;
+    float *out;
+    long long rows_per_z, stride_z, stride_row, stride_col;
+    int m_valid, n_valid, mode, split_k;
+};
+
+__global__ void __launch_bounds__(192)
+umma_gemm_kernel(UmmaGemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (p.k_blocks + p.split_k - 1) / p.split_k;
+    const int kb0 = blockIdx.z * per;
+    const int nkb = min(p.k_blocks, kb0 + per) - kb0;
+    if (nkb <= 0) return;  // uniform for the CTA
+
+    const uint32_t a_bytes = (uint32_t)tile_bytes(TR_A), b_bytes = (uint32_t)tile_bytes(p.trb);
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t bars = base + p.stages * stage_bytes;  // full[stages], empty[stages], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+    const uint32_t accum_bar = bars + 16u * p.stages;
+    const uint32_t tmem_slot = accum_bar + 8u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 4) {
+        if (lane == 0) {
+            const uint8_t *a_src = p.A + ((size_t)blockIdx.x * p.k_blocks + kb0) * a_bytes;
+            const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.k_blocks + kb0) * b_bytes;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                bulk_g2s(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes, full_bar(s));
+                bulk_g2s(base + s * stage_bytes + a_bytes, b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+            const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                tc_fence_after();
+                const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
+#pragma unroll
+                for (int ks = 0; ks < KB / 16; ++ks) {
+                    const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
+                    const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
+                    const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
+                    const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
+                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, (i | ks) != 0);
+                    mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, 1);
+                    mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, 1);
+                }
+                mma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+            }
+            mma_commit(accum_bar);
+        }
+    } else {
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const long long row = (long long)blockIdx.x * TR_A + warp * 32 + lane;
+        const bool row_ok = row < p.m_valid;
+        float *dst_row = p.out;
+        if (row_ok) dst_row += (row / p.rows_per_z) * p.stride_z + (row % p.rows_per_z) * p.stride_row;
+        for (int c0 = 0; c0 < p.trb; c0 += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int col = blockIdx.y * p.trb + c0 + j;
+                if (row_ok && c0 + j < p.trb && col < p.n_valid) {
+                    float *dst = dst_row + (long long)col * p.stride_col;
+                    if (p.mode) atomicAdd(dst, v[j]);
+                    else *dst = v[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+int umma_trb_for(int n_rows) {  // rows per B tile = UMMA N: multiple of 16, at most 256
+    int t = (n_rows + 15) / 16 * 16;
+    return t > 256 ? 256 : t;
+}
+
+int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
+                     const GemmEpilogue &ep, int split_k, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) {
+            set_error("umma_gemm_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr_set = true;
+    }
+    UmmaGemmParams p;
+    p.A = static_cast<const uint8_t *>(A_tiles);
+    p.B = static_cast<const uint8_t *>(B_tiles);
+    p.k_blocks = (int)((K + KB - 1) / KB);
+    p.trb = trb;
+    const size_t stage = tile_bytes(TR_A) + tile_bytes(trb);
+    int stages = (int)((200 * 1024) / stage);
+    if (stages > 4) stages = 4;
+    if (trb <= 128 && stages > 3) stages = 3;  // 2 CTAs per SM
+    if (stages < 2) stages = 2;
+    p.stages = stages;
+    uint32_t cols = 32;
+    while ((int)cols < trb) cols *= 2;
+    p.tmem_cols = cols;
+    p.out = ep.out;
+    p.rows_per_z = ep.rows_per_z;
+    p.stride_z = ep.stride_z;
+    p.stride_row = ep.stride_row;
+    p.stride_col = ep.stride_col;
+    p.m_valid = m_rows;
+    p.n_valid = n_rows;
+    p.mode = ep.atomic ? 1 : 0;
+    if (split_k < 1) split_k = 1;
+    if (split_k > p.k_blocks) split_k = p.k_blocks;
+    p.split_k = split_k;
+    dim3 grid((m_rows + TR_A - 1) / TR_A, (n_rows + trb - 1) / trb, split_k);
+    if (grid.y > 65535 || grid.z > 65535) {
+        set_error("umma_gemm: grid too large");
+        return EPN_ERR_SHAPE;
+    }
+    const size_t smem = (size_t)stages * stage + 128 + 16 * stages + 32;
+    ProfScope prof(s, KC_GEMM);
+    umma_gemm_kernel<<<grid, 192, smem, s>>>(p);
+    return check_launch("umma_gemm_kernel");
+}
+
+}  // namespace epn

@@ -35,6 +35,29 @@ int launch_intra_group_bwd(const float *dgrouped, long long stride_b, long long 
                            const int32_t *intra_idx, float *dfeats, int b, int c, int p, int na, int kn,
                            cudaStream_t s);
 
+// epn_gemm_umma.cu -- tcgen05 path.
+// Source matrix of a split-tile conversion: element (row, k) lives at
+//   ptr + (row / rows_per_z) * stride_rz + (row % rows_per_z) * stride_row
+//       + (k / k_per_z) * stride_kz + (k % k_per_z) * stride_k
+struct SplitSrc {
+    const float *ptr;
+    long long rows_per_z, stride_rz, stride_row;
+    long long k_per_z, stride_kz, stride_k;
+};
+// Where the GEMM writes D[row, col]: out + (row / rows_per_z) * stride_z + (row % rows_per_z) * stride_row
+//                                        + col * stride_col      (atomic: RED add instead of store)
+struct GemmEpilogue {
+    float *out;
+    long long rows_per_z, stride_z, stride_row, stride_col;
+    bool atomic;
+};
+size_t split_tiles_bytes(long long rows, long long K, int tr);
+int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s);
+int umma_trb_for(int n_rows);
+// D[m_rows, n_rows] = A[m_rows, K] * B[n_rows, K]^T on split tiles (A: 128-row tiles, B: trb-row tiles)
+int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
+                     const GemmEpilogue &ep, int split_k, cudaStream_t s);
+
 // epn_gemm_simt.cu
 int launch_sgemm(const GemmOperand &A, const GemmOperand &B, float *C, long long c_stride_z, long long ldc,
                  int M, int N, int K, int batch, int split_k, int accumulate, cudaStream_t s);

@@ -251,8 +251,11 @@ def basic_conv_fwd(x, W):
     b, c, ks, p, na = x.shape
     co = W.shape[0]
     out = torch.empty(b, co, p, na, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().epn_basic_conv_fwd_f32(_p(x), _p(W), _p(out), b, c * ks, co, p * na, _stream()),
+        wsb = L.epn_basic_conv_workspace_bytes(b, c * ks, co, p * na)
+        ws = _workspace(wsb, x.device)
+        _lib.check(L.epn_basic_conv_fwd_f32(_p(x), _p(W), _p(out), _p(ws), wsb, b, c * ks, co, p * na, _stream()),
                    "epn_basic_conv_fwd_f32")
     return out
 
@@ -263,9 +266,12 @@ def basic_conv_bwd(dout, x, W, need_dx=True, need_dw=True):
     co = W.shape[0]
     dx = torch.empty_like(x) if need_dx else None
     dW = torch.empty_like(W) if need_dw else None
+    L = _lib.lib()
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().epn_basic_conv_bwd_f32(_p(dout), _p(x), _p(W), _p(dx), _p(dW), b, c * ks, co, p * na,
-                                                     _stream()), "epn_basic_conv_bwd_f32")
+        wsb = L.epn_basic_conv_workspace_bytes(b, c * ks, co, p * na)
+        ws = _workspace(wsb, x.device)
+        _lib.check(L.epn_basic_conv_bwd_f32(_p(dout), _p(x), _p(W), _p(dx), _p(dW), _p(ws), wsb, b, c * ks, co, p * na,
+                                            _stream()), "epn_basic_conv_bwd_f32")
     return dx, dW
 
 
@@ -344,6 +350,11 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True)
                                                wsb, b, c_in, c_out, p, na, kn, _stream()),
                    "epn_intra_so3conv_bwd_f32")
     return dfeats, dW
+
+
+def set_gemm_backend(name):
+    """'umma' (tcgen05 tensor cores, default) or 'simt' (fp32 cross-check path)."""
+    _lib.lib().epn_set_gemm_backend({"umma": 0, "simt": 1}[name])
 
 
 # ------------------------------------------ drop-in namespaces for vgtk.cuda.*

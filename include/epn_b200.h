@@ -166,12 +166,25 @@ int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32
                               int kn, void *stream);
 
 /* BasicSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:48-55) on an already
- * grouped tensor: x [b, ck, pa], W [co, ck] -> out [b, co, pa]. */
-int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, int b, int ck, int co, int pa,
-                           void *stream);
+ * grouped tensor: x [b, ck, pa], W [co, ck] -> out [b, co, pa].
+ * workspace: epn_basic_conv_workspace_bytes(...) bytes, 256-B aligned (operand tiles). */
+size_t epn_basic_conv_workspace_bytes(int b, int ck, int co, int pa);
+int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, void *workspace,
+                           size_t workspace_bytes, int b, int ck, int co, int pa, void *stream);
 /* dx [b,ck,pa] (NULL to skip), dW [co,ck] (NULL to skip; fully written). */
 int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, float *dx, float *dW,
-                           int b, int ck, int co, int pa, void *stream);
+                           void *workspace, size_t workspace_bytes, int b, int ck, int co, int pa,
+                           void *stream);
+
+/* Channel-GEMM engine used by the three convs: 0 = tcgen05 tensor cores with bf16 hi/lo
+ * operand splitting (default; fp32-faithful to ~1e-5 relative), 1 = fp32 SIMT GEMM (the
+ * in-library cross-check used by the GPU tests; also selectable with EPN_GEMM=simt). */
+void epn_set_gemm_backend(int simt);
+/* Size of the L2-resident grouped slab the convs are scheduled in (default 32 MiB, or the
+ * EPN_SLAB_BYTES environment variable).  Changes the *_workspace_bytes() results. */
+void epn_set_slab_bytes(size_t bytes);
+size_t epn_get_slab_bytes(void);
+int epn_get_gemm_backend(void);
 
 #ifdef __cplusplus
 }

@@ -373,3 +373,74 @@ def test_error_behaviour_on_device(E):
     rc = L.epn_inter_so3conv_fwd_f32(None, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 0.1,
                                      x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, 1, 1, 4, 8, 8, 4, 60, 24, None)
     assert rc == -3 and b"workspace" in L.epn_last_error()
+
+
+# ------------------------------------------- tcgen05 GEMM engine vs the fp32 SIMT cross-check
+@pytest.fixture
+def both_backends(E):
+    yield E.ops.set_gemm_backend
+    E.ops.set_gemm_backend("umma")
+
+
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_", [
+    (4, 8, 96, 2, 16), (64, 64, 512, 1, 16), (64, 128, 512, 2, 32), (128, 256, 256, 2, 32), (256, 256, 128, 1, 16),
+    (3, 20, 70, 1, 8), (1, 64, 1024, 2, 32),
+])
+def test_umma_engine_matches_simt_inter(E, both_backends, c_in, c_out, p_in, stride, nn_):
+    """bf16 hi/lo split (3 MMAs) on tcgen05 vs exact fp32 FMA GEMM: forward, dfeats and dW."""
+    conv = _layer(E, c_in, c_out, stride, nn_, 0.45, 0.1)
+    xyz = sphere(2, p_in, 21).to(DEV)
+    res = {}
+    for be in ("simt", "umma"):
+        both_backends(be)
+        f = torch.randn(2, c_in, p_in, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(3)).requires_grad_(True)
+        conv.zero_grad()
+        _, _, _, y = conv(E.SphericalPointCloud(xyz, f, None))
+        r = torch.randn(y.feats.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(4))
+        (y.feats * r).sum().backward()
+        res[be] = (y.feats.detach(), f.grad.detach(), conv.basic_conv.W.grad.detach().clone())
+    for a, b_, name in zip(res["umma"], res["simt"], ("out", "dfeats", "dW")):
+        assert rel_err(a, b_) < 3e-5, name
+
+
+@pytest.mark.parametrize("c_in,c_out,p", [(4, 8, 32), (64, 64, 512), (128, 128, 256), (256, 256, 128), (5, 300, 17)])
+def test_umma_engine_matches_simt_intra(E, both_backends, c_in, c_out, p):
+    torch.manual_seed(0)
+    conv = E.IntraSO3Conv(c_in, c_out).to(DEV)
+    res = {}
+    for be in ("simt", "umma"):
+        both_backends(be)
+        f = torch.randn(2, c_in, p, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(5)).requires_grad_(True)
+        conv.zero_grad()
+        y = conv(E.SphericalPointCloud(None, f, None)).feats
+        r = torch.randn(y.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(6))
+        (y * r).sum().backward()
+        res[be] = (y.detach(), f.grad.detach(), conv.basic_conv.W.grad.detach().clone())
+    for a, b_, name in zip(res["umma"], res["simt"], ("out", "dfeats", "dW")):
+        assert rel_err(a, b_) < 3e-5, name
+
+
+def test_umma_engine_many_slabs(E, both_backends, monkeypatch):
+    """Force the slab scheduler to cut clouds into several point ranges (tile tails, row->(z,j) mapping)."""
+    from epn_pointcloud_b200 import _lib
+    L = _lib.lib()
+    conv = _layer(E, 16, 24, 1, 16, 0.45, 0.1)
+    xyz = sphere(3, 100, 22).to(DEV)
+    old = L.epn_get_slab_bytes()
+    res = {}
+    try:
+        for slab in (old, 1 << 20, 200 << 10):   # all clouds in one slab / 11 points per slab / 2 points per slab
+            L.epn_set_slab_bytes(slab)
+            for be in ("simt", "umma"):
+                both_backends(be)
+                f = torch.randn(3, 16, 100, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(8)).requires_grad_(True)
+                conv.zero_grad()
+                _, _, _, y = conv(E.SphericalPointCloud(xyz, f, None))
+                y.feats.square().sum().backward()
+                res[(slab, be)] = (y.feats.detach(), f.grad.detach(), conv.basic_conv.W.grad.detach().clone())
+    finally:
+        L.epn_set_slab_bytes(old)
+    ref = res[(old, "simt")]
+    for key, val in res.items():
+        for a, b_, name in zip(val, ref, ("out", "dfeats", "dW")):
+            assert rel_err(a, b_) < 3e-5, (key, name)
