@@ -78,9 +78,9 @@ def inter_so3conv(xyz, feats, W, anchors, kernels, stride, n_neighbor, radius, s
     (incl. the zero shadow row appended at :174, spconv/functional.py:91-95).
     Returns (inter_idx, inter_w, sample_idx, new_xyz, out)."""
     grouped_xyz, inter_idx, sample_idx, new_xyz = sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample)
-    inter_w = inter_weights(grouped_xyz, anchors, kernels, sigma)
+    inter_w = inter_weights(grouped_xyz.to(feats.dtype), anchors.to(feats.dtype), kernels.to(feats.dtype), sigma)
     b, c, _, a = feats.shape
-    feats_sh = torch.cat((feats, torch.zeros(b, c, 1, a)), dim=2).contiguous()
+    feats_sh = torch.cat((feats, torch.zeros(b, c, 1, a, dtype=feats.dtype)), dim=2).contiguous()
     grouped = inter_group(inter_idx, inter_w, feats_sh)
     return inter_idx, inter_w, sample_idx, new_xyz, basic_conv(grouped, W)
 
@@ -121,14 +121,14 @@ def separable_block(xyz, feats, prm, args, intra_idx, anchors, kernels):
     return new_xyz, x + skip
 
 
-def backbone_forward(x, layers):
+def backbone_forward(x, layers, dtype=torch.float32):
     """ClsSO3ConvModel.forward minus the head (SPConvNets/models/cls_so3net_pn.py:27-33;
     preprocess_input base_so3conv.py:16-23 with add_center=False).
     x [b,n,3]; layers: list of (prm, args, intra_idx, anchors, kernels)."""
     b, n, _ = x.shape
     xyz = x.permute(0, 2, 1).contiguous()
     na = layers[0][3].shape[0]
-    feats = torch.ones(b, 1, n, na)
+    feats = torch.ones(b, 1, n, na, dtype=dtype)  # dtype=float64 gives the "true" value the fp32 paths round
     for prm, args, intra_idx, anchors, kernels in layers:
         xyz, feats = separable_block(xyz, feats, prm, args, intra_idx, anchors, kernels)
     return xyz, feats
