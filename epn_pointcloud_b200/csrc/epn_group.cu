@@ -82,7 +82,7 @@ inter_weights_kernel(InterGeom g, const int32_t *__restrict__ idx, float *__rest
 template <int KG, int NN>
 __device__ __forceinline__ void load_w(float (&w)[KG][NN], const float *__restrict__ inter_w_pt,
                                        const float *s_g, const float (&rx)[KG], const float (&ry)[KG],
-                                       const float (&rz)[KG], float inv_sigma, int a, int k0, int n0,
+                                       const float (&rz)[KG], float sigma, int a, int k0, int n0,
                                        int nn, int ks, bool a_ok) {
 #pragma unroll
     for (int i = 0; i < KG; ++i) {
@@ -94,10 +94,8 @@ __device__ __forceinline__ void load_w(float (&w)[KG][NN], const float *__restri
                 if (inter_w_pt != nullptr) {
                     v = __ldg(inter_w_pt + ((size_t)a * ks + k0 + i) * nn + n0 + n);
                 } else {
-                    const float dx = s_g[(n0 + n) * 3] - rx[i], dy = s_g[(n0 + n) * 3 + 1] - ry[i],
-                                dz = s_g[(n0 + n) * 3 + 2] - rz[i];
-                    const float d = dx * dx + dy * dy + dz * dz;
-                    v = fmaxf(fmaf(-d, inv_sigma, 1.0f), 0.0f);
+                    v = kernel_weight(s_g[(n0 + n) * 3], s_g[(n0 + n) * 3 + 1], s_g[(n0 + n) * 3 + 2], rx[i], ry[i],
+                                      rz[i], sigma);
                 }
             }
             w[i][n] = v;
@@ -131,7 +129,6 @@ inter_group_fwd_kernel(const float *__restrict__ feats, const int32_t *__restric
     const int b = blockIdx.y;
     const bool a_ok = a < na;
     const int aa = a_ok ? a : 0;
-    const float inv_sigma = 1.0f / g.sigma;
     const float *F = feats ? feats + (size_t)b * c * p_in * na : nullptr;
     const int kgroups = (ks + KG - 1) / KG;
 
@@ -157,7 +154,7 @@ inter_group_fwd_kernel(const float *__restrict__ feats, const int32_t *__restric
             if (inter_w == nullptr) rotated_kernels<KG>(g, aa, k0, ks, rx, ry, rz);
             for (int n0 = 0; n0 < nn; n0 += NN) {
                 float w[KG][NN];
-                load_w<KG, NN>(w, wpt, s_g, rx, ry, rz, inv_sigma, aa, k0, n0, nn, ks, a_ok);
+                load_w<KG, NN>(w, wpt, s_g, rx, ry, rz, g.sigma, aa, k0, n0, nn, ks, a_ok);
                 for (int ci = 0; ci < c; ++ci) {
                     float f[NN];
 #pragma unroll
@@ -205,7 +202,6 @@ inter_group_bwd_kernel(const float *__restrict__ dgrouped, long long d_stride_b,
     const int b = blockIdx.y;
     const bool a_ok = a < na;
     const int aa = a_ok ? a : 0;
-    const float inv_sigma = 1.0f / g.sigma;
     float *DF = dfeats + (size_t)b * c * p_in * na;
     float R[9];
 #pragma unroll
@@ -250,9 +246,8 @@ inter_group_bwd_kernel(const float *__restrict__ dgrouped, long long d_stride_b,
                             if (inter_w != nullptr) {
                                 v = __ldg(wpt + ((size_t)a * ks + kb + k) * nn + n0 + n);
                             } else {
-                                const float dx = s_g[(n0 + n) * 3] - rx, dy = s_g[(n0 + n) * 3 + 1] - ry,
-                                            dz = s_g[(n0 + n) * 3 + 2] - rz;
-                                v = fmaxf(fmaf(-(dx * dx + dy * dy + dz * dz), inv_sigma, 1.0f), 0.0f);
+                                v = kernel_weight(s_g[(n0 + n) * 3], s_g[(n0 + n) * 3 + 1], s_g[(n0 + n) * 3 + 2], rx, ry,
+                                                  rz, g.sigma);
                             }
                         }
                         w[k][n] = v;

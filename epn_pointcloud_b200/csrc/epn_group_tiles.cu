@@ -80,7 +80,6 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
         float R[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
-        const float inv_sigma = 1.0f / g.sigma;
 #pragma unroll
         for (int i = 0; i < KG; ++i) {
             const float kx = __ldg(g.kernels + (k0 + i) * 3), ky = __ldg(g.kernels + (k0 + i) * 3 + 1),
@@ -89,8 +88,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
                         rz = R[6] * kx + R[7] * ky + R[8] * kz;
 #pragma unroll
             for (int n = 0; n < NN; ++n) {
-                const float dx = s_g[n * 3] - rx, dy = s_g[n * 3 + 1] - ry, dz = s_g[n * 3 + 2] - rz;
-                const float v = fmaxf(fmaf(-(dx * dx + dy * dy + dz * dz), inv_sigma, 1.0f), 0.0f);
+                const float v = kernel_weight(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, g.sigma);
                 w[i][n] = (a_ok && n < nn) ? v : 0.f;
             }
         }

@@ -12,6 +12,16 @@ struct InterGeom {
     float sigma;
 };
 
+// Kernel weight relu(1 - |g - r|^2 / sigma) in the reference's fp32 operation order
+// (so3conv/functional.py:198-200: square, (x+y)+z, true division, subtract; no FMA contraction), so the
+// weights agree with the reference to the last bit for identical rotated kernel points.
+__device__ __forceinline__ float kernel_weight(float gx, float gy, float gz, float rx, float ry, float rz,
+                                               float sigma) {
+    const float dx = gx - rx, dy = gy - ry, dz = gz - rz;
+    const float d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return fmaxf(__fsub_rn(1.0f, __fdiv_rn(d, sigma)), 0.0f);
+}
+
 // Matrix operand of the generic GEMM: element (row, col) of slice z lives at
 // ptr + z*stride_z + row*stride_row + col*stride_col.  For A rows are m and
 // cols are k; for B rows are k and cols are n.
