@@ -374,8 +374,12 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
             if (dfeats != nullptr) {
                 // dG = W^T . dout, then scatter through the transposed spatial contraction
                 EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
-                EPN_TRY(launch_inter_group_bwd(ws.slab, cols, n_slab, p0, pc, idx_b, nullptr, g,
-                                               dfeats + (size_t)b0 * c_in * p_in * na, bc, c_in, p_in, p, nn, na, ks, s));
+                int sc = launch_inter_scatter(ws.slab, cols, n_slab, idx_b, g, dfeats + (size_t)b0 * c_in * p_in * na, p0, pc,
+                                              bc, c_in, p_in, p, nn, na, ks, s);
+                if (sc == 1)
+                    sc = launch_inter_group_bwd(ws.slab, cols, n_slab, p0, pc, idx_b, nullptr, g,
+                                                dfeats + (size_t)b0 * c_in * p_in * na, bc, c_in, p_in, p, nn, na, ks, s);
+                if (sc != 0) return sc;
             }
             if (dW != nullptr) {
                 // dW += dout . G^T with G recomputed (never saved by the forward)
@@ -425,11 +429,21 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
         for (int p0 = 0; p0 < p; p0 += sp.pc) {
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
             const long long cols = (long long)pc * na, n_slab = bc * cols;
-            EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0, pc,
-                                           bc, c_in, p, na, kn, s));
-            ColsView in{ws.slab, cols, n_slab};
             ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
-            EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
+            int direct = 1;
+            if (gemm_backend() == 0) {
+                direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.tilesA, 0, p0, pc, bc, c_in,
+                                                  p, na, kn, s);
+                if (direct != 0 && direct != 1) return direct;
+            }
+            if (direct == 0) {
+                EPN_TRY(gemm_fwd_tiles(c_out, ck, bc, cols, o, ws, s));
+            } else {
+                EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0, pc,
+                                               bc, c_in, p, na, kn, s));
+                ColsView in{ws.slab, cols, n_slab};
+                EPN_TRY(gemm_fwd(W, c_out, ck, in, bc, cols, o, ws, s));
+            }
         }
     }
     return 0;
@@ -465,9 +479,19 @@ EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, con
                                                dfeats + (size_t)b0 * c_in * p * na, bc, c_in, p, na, kn, s));
             }
             if (dW != nullptr) {
-                EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0,
-                                               pc, bc, c_in, p, na, kn, s));
-                EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
+                int direct = 1;
+                if (gemm_backend() == 0) {
+                    direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.tilesA, 1, p0, pc, bc,
+                                                      c_in, p, na, kn, s);
+                    if (direct != 0 && direct != 1) return direct;
+                }
+                if (direct == 0) {
+                    EPN_TRY(gemm_dw_tiles(d, c_out, ck, bc, cols, dW, ws, s));
+                } else {
+                    EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0,
+                                                   pc, bc, c_in, p, na, kn, s));
+                    EPN_TRY(gemm_dw(d, slab, c_out, ck, bc, cols, dW, ws, s));
+                }
             }
         }
     }

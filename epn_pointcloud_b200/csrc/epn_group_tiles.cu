@@ -95,33 +95,42 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     }
 
     const int nchunks = (c + CCH - 1) / CCH;
-    const int segs = na / 4;  // 16-byte segments per feature row (na % 4 == 0)
+    // Gather = one bulk async copy (UBLKCP) per neighbour feature row (4*na contiguous bytes), completing
+    // on the mbarrier of the stage buffer; thread t issues row (channel t / NN, neighbour t % NN).
+    __shared__ __align__(8) uint64_t s_bar[2];
     const uint32_t fs_u32 = smem_u32(Fs);
+    const uint32_t bar0 = smem_u32(&s_bar[0]);  // buffer b uses the barrier at bar0 + 8*b
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const uint32_t row_bytes = (uint32_t)na * 4u;
     auto issue = [&](int chunk, int buf) {
-        if (F != nullptr) {
-            const int total = CCH * nn * segs;
-            for (int t = tid; t < total; t += nthr) {
-                const int seg = t % segs, rn = t / segs, n = rn % nn, cl = rn / nn;
-                const int cc = chunk * CCH + cl;
-                if (cc < c)
-                    cp_async16(fs_u32 + (uint32_t)((((buf * CCH + cl) * NN + n) * GT_FROW + seg * 4) * 4),
-                               F + ((size_t)cc * p_in + s_idx[n]) * na + seg * 4);
-            }
+        if (F == nullptr) return;
+        const int nch = min(CCH, c - chunk * CCH);
+        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nch * nn) * row_bytes);
+        for (int t = tid; t < nch * NN; t += nthr) {
+            const int cl = t / NN, n = t % NN;
+            if (n < nn)
+                bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * GT_FROW) * 4u,
+                         F + ((size_t)(chunk * CCH + cl) * p_in + s_idx[n]) * na, row_bytes, bar);
         }
-        cp_async_commit();
     };
 
     const long long col0 = (long long)z * out.cols_per_z + (long long)pl * na;
+    uint32_t phase_bits = 0u;  // bit b = parity to wait for on buffer b
     issue(0, 0);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int buf = chunk & 1;
-        if (chunk + 1 < nchunks) {
-            issue(chunk + 1, buf ^ 1);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
+        if (F != nullptr) {
+            mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
+            phase_bits ^= 1u << buf;
         }
-        __syncthreads();  // staged rows visible; previous conversion finished reading Gs
+        __syncthreads();  // previous conversion finished reading Gs
 
         // ---- spatial contraction of CCH channels
         for (int cl = 0; cl < CCH; ++cl) {

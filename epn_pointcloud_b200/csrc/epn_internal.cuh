@@ -50,6 +50,13 @@ int launch_inter_group_tiles(const float *feats, const int32_t *idx, const Inter
                              int row_limit, long long cols_per_z, int mode, int p_off, int p_cnt, int bc, int c,
                              int p_in, int p, int nn, int na, int ks, cudaStream_t s);
 
+// epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
+int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
+                             int bc, int c, int p, int na, int kn, cudaStream_t s);
+int launch_inter_scatter(const float *dG, long long stride_b, long long stride_ck, const int32_t *idx,
+                         const InterGeom &g, float *dfeats, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn,
+                         int na, int ks, cudaStream_t s);
+
 // epn_gemm_umma.cu -- tcgen05 path.
 // Source matrix of a split-tile conversion: element (row, k) lives at
 //   ptr + (row / rows_per_z) * stride_rz + (row % rows_per_z) * stride_row

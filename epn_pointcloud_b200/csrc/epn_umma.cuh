@@ -131,11 +131,12 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        // one packed cvt.rn.bf16x2.f32 per pair (element 2i in the low half), bf16 -> f32 is a shift / mask
+        const __nv_bfloat162 hp = __floats2bfloat162_rn(x[2 * i], x[2 * i + 1]);
+        h[i] = *reinterpret_cast<const uint32_t *>(&hp);
+        const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xffff0000u);
+        const __nv_bfloat162 lp = __floats2bfloat162_rn(x[2 * i] - h0, x[2 * i + 1] - h1);
+        l[i] = *reinterpret_cast<const uint32_t *>(&lp);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
