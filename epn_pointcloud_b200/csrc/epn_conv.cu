@@ -90,13 +90,14 @@ static Workspace carve(void *base, int ck, int c_out, long long n_slab, bool nee
     };
     w.slab = reinterpret_cast<float *>(take(need_slab ? (size_t)ck * n_slab * sizeof(float) : 0));
     size_t a = split_tiles_bytes(n_slab, ck, 128);
-    const size_t a2 = split_tiles_bytes(n_slab, c_out, 128), a3 = split_tiles_bytes(ck, n_slab, 128);
+    const size_t a2 = split_tiles_bytes(n_slab, c_out, 256) + split_tiles_bytes(256, c_out, 256),
+                 a3 = split_tiles_bytes(ck, n_slab, 128);
     if (a2 > a) a = a2;
     if (a3 > a) a = a3;
     w.tilesA = take(a);
     w.tilesB = take(split_tiles_bytes(c_out, n_slab, umma_trb_for(c_out)));
     w.tilesW = take(split_tiles_bytes(c_out, ck, umma_trb_for(c_out)));
-    w.tilesWT = take(split_tiles_bytes(ck, c_out, umma_trb_for(ck)));
+    w.tilesWT = take(split_tiles_bytes(ck, c_out, 128));
     w.total = off;
     return w;
 }
@@ -118,7 +119,7 @@ static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, 
     }
     if (transposed) {
         SplitSrc src{W, HUGE_Z, 0, 1, HUGE_Z, 0, ck};
-        int rc = launch_split_tiles(src, ws.tilesWT, ck, c_out, umma_trb_for(ck), s);
+        int rc = launch_split_tiles(src, ws.tilesWT, ck, c_out, 128, s);
         if (rc) return rc;
     }
     return 0;
@@ -179,12 +180,17 @@ static int gemm_dx(const float *W, int c_out, int ck, ColsView dout, int bc, lon
         GemmOperand B{dout.ptr, dout.stride_z, dout.stride_k, 1};
         return launch_sgemm(A, B, din.ptr, din.stride_z, din.stride_k, ck, (int)cols, c_out, bc, 1, 0, s);
     }
+    // orientation: D[rows = (c,k), cols = (z,j)] so that an epilogue thread owns one (c,k) row and writes
+    // runs of consecutive columns as 16-byte vectors (din is column-contiguous)
     const long long n = bc * cols;
+    const int trn = umma_trb_for((int)(n < 256 ? n : 256));
     SplitSrc src{dout.ptr, cols, dout.stride_z, 1, HUGE_Z, 0, dout.stride_k};
-    int rc = launch_split_tiles(src, ws.tilesA, n, c_out, 128, s);
+    int rc = launch_split_tiles(src, ws.tilesA, n, c_out, trn, s);
     if (rc) return rc;
-    GemmEpilogue ep{din.ptr, cols, din.stride_z, 1, din.stride_k, false};
-    return launch_umma_gemm(ws.tilesA, ws.tilesWT, (int)n, ck, c_out, umma_trb_for(ck), ep, 1, s);
+    GemmEpilogue ep{din.ptr, HUGE_Z, 0, din.stride_k, 1, false};
+    ep.cols_per_z = cols;
+    ep.stride_cz = din.stride_z;
+    return launch_umma_gemm(ws.tilesWT, ws.tilesA, ck, (int)n, c_out, trn, ep, 1, s);
 }
 
 // dW(c_out x ck) += dout(c_out) . in(ck)^T      (dW pre-zeroed by the caller)

@@ -81,8 +81,8 @@ struct UmmaGemmParams {
     int k_blocks, trb, stages;
     uint32_t tmem_cols;
     float *out;
-    long long rows_per_z, stride_z, stride_row, stride_col;
-    int m_valid, n_valid, mode, split_k;
+    long long rows_per_z, stride_z, stride_row, stride_col, cols_per_z, stride_cz;
+    int m_valid, n_valid, mode, split_k, vec;
 };
 
 __global__ void __launch_bounds__(192)
@@ -162,16 +162,40 @@ umma_gemm_kernel(UmmaGemmParams p) {
         const bool row_ok = row < p.m_valid;
         float *dst_row = p.out;
         if (row_ok) dst_row += (row / p.rows_per_z) * p.stride_z + (row % p.rows_per_z) * p.stride_row;
+        const bool col_split = p.cols_per_z < (long long)p.n_valid;  // columns run over (cloud, point*anchor)
+        const uint32_t cpz = col_split ? (uint32_t)p.cols_per_z : 1u;
+        auto col_offset = [&](uint32_t col, long long stride_col) -> long long {
+            if (!col_split) return (long long)col * stride_col;
+            const uint32_t cz = col / cpz;
+            return (long long)cz * p.stride_cz + (long long)(col - cz * cpz) * stride_col;
+        };
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            const long long colb = (long long)blockIdx.y * p.trb + c0;
+            if (p.vec) {
+                // output columns are contiguous in memory: the thread's 32 values go out as 8 x 16 bytes
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int col = blockIdx.y * p.trb + c0 + j;
-                if (row_ok && c0 + j < p.trb && col < p.n_valid) {
-                    float *dst = dst_row + (long long)col * p.stride_col;
-                    if (p.mode) atomicAdd(dst, v[j]);
-                    else *dst = v[j];
+                for (int j = 0; j < 32; j += 4) {
+                    const long long col = colb + j;
+                    if (row_ok && c0 + j < p.trb && col < p.n_valid) {
+                        float *dst = dst_row + col_offset((uint32_t)col, 1);
+                        if (col + 3 < p.n_valid) {
+                            *reinterpret_cast<float4 *>(dst) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+                            for (int t = 0; t < 4 && col + t < p.n_valid; ++t) dst[t] = v[j + t];
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const long long col = colb + j;
+                    if (row_ok && c0 + j < p.trb && col < p.n_valid) {
+                        float *dst = dst_row + col_offset((uint32_t)col, p.stride_col);
+                        if (p.mode) atomicAdd(dst, v[j]);
+                        else *dst = v[j];
+                    }
                 }
             }
         }
@@ -209,6 +233,8 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     int stages = (int)((200 * 1024) / stage);
     if (stages > 4) stages = 4;
     if (trb <= 128 && stages > 3) stages = 3;  // 2 CTAs per SM
+    if (trb > 128) stages = 2;                 // 96 KB per CTA: 2 CTAs per SM (2 x 256 TMEM columns), the
+                                               // epilogue of one overlaps the main loop of the other
     if (stages < 2) stages = 2;
     p.stages = stages;
     uint32_t cols = 32;
@@ -219,6 +245,14 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     p.stride_z = ep.stride_z;
     p.stride_row = ep.stride_row;
     p.stride_col = ep.stride_col;
+    p.cols_per_z = ep.cols_per_z;
+    p.stride_cz = ep.stride_cz;
+    if (ep.stride_col == 1 && ep.stride_cz == ep.cols_per_z) {  // (z, j) columns are contiguous after all
+        p.cols_per_z = 1LL << 60;
+        p.stride_cz = 0;
+    }
+    p.vec = (!ep.atomic && ep.stride_col == 1 && (ep.cols_per_z % 4) == 0 && (ep.stride_cz % 4) == 0 &&
+             (ep.stride_row % 4) == 0 && (ep.stride_z % 4) == 0 && ((uintptr_t)ep.out & 15) == 0) ? 1 : 0;
     p.m_valid = m_rows;
     p.n_valid = n_rows;
     p.mode = ep.atomic ? 1 : 0;

@@ -68,10 +68,13 @@ struct SplitSrc {
 };
 // Where the GEMM writes D[row, col]: out + (row / rows_per_z) * stride_z + (row % rows_per_z) * stride_row
 //                                        + col * stride_col      (atomic: RED add instead of store)
+//   + (col / cols_per_z) * stride_cz for outputs whose COLUMN index runs over (cloud, point*anchor).
+// When stride_col == 1 (and cols_per_z % 4 == 0) the epilogue writes 16-byte vectors.
 struct GemmEpilogue {
     float *out;
     long long rows_per_z, stride_z, stride_row, stride_col;
     bool atomic;
+    long long cols_per_z = 1LL << 60, stride_cz = 0;
 };
 size_t split_tiles_bytes(long long rows, long long K, int tr);
 int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s);
