@@ -470,3 +470,44 @@ def test_umma_engine_many_slabs(E, both_backends, monkeypatch):
     for key, val in res.items():
         for a, b_, name in zip(val, ref, ("out", "dfeats", "dW")):
             assert rel_err(a, b_) < 3e-5, (key, name)
+
+
+# ------------------------------ shapes of the other BASELINE configs (rotation model, 3DMatch model, sweep)
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,radius,sigma,kanchor", [
+    (32, 32, 512, 1, 32, 0.2828, 0.04, 60),      # reg model b0l1 (K=32)
+    (32, 64, 512, 2, 64, 0.4, 0.08, 60),         # reg model b1l0 (K=64 -> generic grouping path)
+    (1, 32, 2048, 4, 128, 0.08, 0.0032, 60),     # inv model layer 0 (2048 pts, stride 4, K=128, FPS)
+    (32, 32, 512, 1, 32, 0.113, 0.0128, 60),     # inv model layer 1
+    (16, 16, 256, 1, 32, 0.7, 0.25, 12),         # sweep: A=12 (first 12 anchors, inter conv only)
+    (8, 8, 256, 1, 16, 0.5, 0.125, 20),          # config 1 anchor count with real features
+])
+def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, radius, sigma, kanchor):
+    """Forward + gradients of one InterSO3Conv against the CPU oracle port (reference op chain) on one cloud."""
+    from oracle import torch_port as TP
+    torch.manual_seed(1)
+    conv = E.InterSO3Conv(c_in, c_out, 1, stride, radius, sigma, nn_, lazy_sample=(c_in != 1), kanchor=60).to(DEV)
+    if kanchor != 60:  # anchor subsets: select_anchor (so3conv/functional.py:281-289) or the sweep's "first 12"
+        from epn_pointcloud_b200 import functional as L
+        anchors = L.get_anchors(kanchor) if kanchor in (1, 20, 40) else L.get_anchors(60)[:kanchor]
+        conv.anchors = torch.from_numpy(anchors.copy()).to(DEV)
+    surface = c_in != 1 or p_in <= 1024
+    xyz = sphere(1, p_in, 31 + p_in, surface=surface)
+    if p_in == 2048:
+        xyz = xyz * 0.4   # 3DMatch patches live in a ball of radius 0.4 (search_radius)
+    feats = torch.randn(1, c_in, p_in, kanchor, generator=torch.Generator().manual_seed(7))
+    if c_in == 1:
+        feats = torch.ones(1, 1, p_in, kanchor)
+    fg = feats.to(DEV).requires_grad_(True)
+    idx, _, sidx, y = conv(E.SphericalPointCloud(xyz.to(DEV), fg, None))
+    W = conv.basic_conv.W.detach().cpu().requires_grad_(True)
+    fc = feats.clone().requires_grad_(True)
+    ridx, _, rsidx, _, ry = TP.inter_so3conv(xyz, fc, W, conv.anchors.cpu(), conv.kernels.cpu(), stride, nn_, radius, sigma,
+                                             lazy_sample=(c_in != 1))
+    assert torch.equal(idx.cpu(), ridx) and (sidx is None or torch.equal(sidx.cpu(), rsidx))
+    assert rel_err(y.feats, ry) < FEAT_TOL
+    r = torch.randn(ry.shape, generator=torch.Generator().manual_seed(8))
+    (ry * r).sum().backward()
+    (y.feats * r.to(DEV)).sum().backward()
+    assert rel_err(conv.basic_conv.W.grad, W.grad) < FEAT_TOL
+    if c_in != 1:
+        assert rel_err(fg.grad, fc.grad) < FEAT_TOL
