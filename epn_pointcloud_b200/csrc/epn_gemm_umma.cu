@@ -161,7 +161,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
         const long long row = (long long)blockIdx.x * TR_A + warp * 32 + lane;
         const bool row_ok = row < p.m_valid;
         float *dst_row = p.out;
-        if (row_ok) dst_row += (row / p.rows_per_z) * p.stride_z + (row % p.rows_per_z) * p.stride_row;
+        if (row_ok) dst_row += (row / p.rows_per_z) * p.stride_z + (row % p.rows_per_z) * p.stride_row;  // once per thread
         const bool col_split = p.cols_per_z < (long long)p.n_valid;  // columns run over (cloud, point*anchor)
         const uint32_t cpz = col_split ? (uint32_t)p.cols_per_z : 1u;
         auto col_offset = [&](uint32_t col, long long stride_col) -> long long {
@@ -169,6 +169,49 @@ umma_gemm_kernel(UmmaGemmParams p) {
             const uint32_t cz = col / cpz;
             return (long long)cz * p.stride_cz + (long long)(col - cz * cpz) * stride_col;
         };
+        const bool row_split = p.rows_per_z < (long long)p.m_valid;
+        auto row_offset = [&](long long r) -> long long {
+            if (!row_split) return r * p.stride_row;
+            const uint32_t rz = (uint32_t)r / (uint32_t)p.rows_per_z;
+            return (long long)rz * p.stride_z + (long long)((uint32_t)r - rz * (uint32_t)p.rows_per_z) * p.stride_row;
+        };
+        // Column-contiguous outputs (dX): transpose through shared memory (the pipeline stages are free once
+        // the accumulator is complete) so that every warp store is one 512-byte row segment instead of 32
+        // scattered 16-byte pieces.
+        const int gw = p.trb < 128 ? p.trb : 128;  // columns per staged group
+        if (p.vec && (size_t)4 * 32 * (gw + 4) * sizeof(float) <= (size_t)p.stages * stage_bytes) {
+            float *stg = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw))) + (size_t)warp * 32 * (gw + 4);
+            const long long row0 = (long long)blockIdx.x * TR_A + warp * 32;
+            for (int g0 = 0; g0 < p.trb; g0 += gw) {
+                for (int cc = 0; cc < gw; cc += 32) {
+                    float v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g0 + cc), v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (cc + j < gw)
+                            *reinterpret_cast<float4 *>(stg + (size_t)lane * (gw + 4) + cc + j) =
+                                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                __syncwarp();
+                const long long col = (long long)blockIdx.y * p.trb + g0 + 4 * lane;
+                if (4 * lane < gw && g0 + 4 * lane < p.trb && col < p.n_valid) {
+                    const long long coff = col_offset((uint32_t)col, 1);
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const long long r = row0 + rr;
+                        if (r >= p.m_valid) break;
+                        float *dst = p.out + row_offset(r) + coff;
+                        const float4 val = *reinterpret_cast<const float4 *>(stg + (size_t)rr * (gw + 4) + 4 * lane);
+                        if (col + 3 < p.n_valid) {
+                            *reinterpret_cast<float4 *>(dst) = val;
+                        } else {
+                            const float t[4] = {val.x, val.y, val.z, val.w};
+                            for (int e = 0; e < 4 && col + e < p.n_valid; ++e) dst[e] = t[e];
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        } else
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
