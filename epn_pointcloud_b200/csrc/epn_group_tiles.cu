@@ -40,11 +40,14 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     constexpr int GSTR = NA + 1;       // odd staging stride: conflict-free for both conversion mappings
     constexpr int CKK = CCH * GT_KS;   // (c,k) rows produced per chunk (multiple of 32)
     extern __shared__ __align__(16) float s_dyn[];
-    float *s_g = s_dyn;                                            // [NN][3]
-    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]
-    float *Fs = s_dyn + NN * 4;                                    // [2][CCH][NN][NA]
+    float *s_g = s_dyn;                                            // [NN][3]  unique neighbour offsets
+    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]     unique neighbour indices
+    float *s_mult = s_dyn + NN * 4;                                // [NN]     their multiplicities
+    int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     the ball-query row as stored
+    float *Fs = s_dyn + NN * 6;                                    // [2][CCH][NN][NA]
     float *Gs = Fs + 2 * CCH * NN * NA;                            // [CKK][GSTR]
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_nu;
     const int tid = threadIdx.x;
     const int a = tid % GT_LANES, grp = tid / GT_LANES;
     const int k0 = grp * KG;
@@ -53,24 +56,36 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
     const float *F = feats ? feats + (size_t)z * c * p_in * NA : nullptr;
 
-    for (int n = tid; n < NN; n += NTHR) {
-        int q = 0;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (n < nn) {
-            q = idx[((size_t)z * p + pi) * nn + n];
+    // The ball query repeat-fills short neighbour lists cyclically (grouping_cuda_kernel.cu:100-104), so a row
+    // usually holds each neighbour several times.  Duplicates have identical offsets and therefore identical
+    // kernel weights: keep each distinct neighbour once with its multiplicity folded into the weight
+    // (sum_n w_n f_n == sum_u m_u w_u f_u) -- fewer rows to gather and fewer FMAs, same result.
+    for (int n = tid; n < NN; n += NTHR) s_raw[n] = n < nn ? idx[((size_t)z * p + pi) * nn + n] : -1;
+    __syncthreads();
+    if (tid < 32) {  // nn <= 32: one warp de-duplicates the row, keeping first-occurrence order
+        const int n = tid;
+        const int q = n < nn ? s_raw[n] : -1;
+        bool uniq = n < nn;
+        for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
+        int mult = 0;
+        for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, uniq);
+        const int pos = __popc(mask & ((1u << n) - 1u));
+        if (uniq) {
             const float *X = g.xyz + (size_t)z * 3 * p_in;
             const float *Cn = g.centers + (size_t)z * 3 * p;
-            gx = X[q] - Cn[pi];
-            gy = X[p_in + q] - Cn[p + pi];
-            gz = X[2 * p_in + q] - Cn[2 * p + pi];
+            s_idx[pos] = q;
+            s_mult[pos] = (float)mult;
+            s_g[pos * 3] = X[q] - Cn[pi];
+            s_g[pos * 3 + 1] = X[p_in + q] - Cn[p + pi];
+            s_g[pos * 3 + 2] = X[2 * p_in + q] - Cn[2 * p + pi];
         }
-        s_idx[n] = q;
-        s_g[n * 3] = gx; s_g[n * 3 + 1] = gy; s_g[n * 3 + 2] = gz;
-    }
-    // rows of neighbours that do not exist (n >= nn) are never copied: keep them zero in both buffers
-    for (int t = tid; t < 2 * CCH * (NN - nn) * NA; t += NTHR) {
-        const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
-        Fs[(bc * NN + n) * NA + e] = 0.f;
+        const int cnt = __popc(mask);
+        if (n >= cnt && n < NN) {
+            s_idx[n] = 0; s_mult[n] = 0.f;
+            s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
+        }
+        if (n == 0) s_nu = cnt;
     }
     const uint32_t bar0 = smem_u32(&s_bar[0]);  // buffer b uses the barrier at bar0 + 8*b
     if (tid == 0) {
@@ -79,6 +94,13 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
         fence_barrier_init();
     }
     __syncthreads();
+    nn = s_nu;  // from here on: number of DISTINCT neighbours
+    // rows beyond the distinct neighbours are never copied: keep them zero in both buffers (the FMA loop runs
+    // in groups of 4 neighbours and multiplies them by zero weights)
+    for (int t = tid; t < 2 * CCH * (NN - nn) * NA; t += NTHR) {
+        const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
+        Fs[(bc * NN + n) * NA + e] = 0.f;
+    }
 
     // kernel weights of this thread's (anchor, kernel-point group): registers for the whole point
     float w[KG][NN];
@@ -95,7 +117,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
 #pragma unroll
             for (int n = 0; n < NN; ++n) {
                 const float v = kernel_weight(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, g.sigma);
-                w[i][n] = (a_ok && n < nn) ? v : 0.f;
+                w[i][n] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
             }
         }
     }
@@ -143,10 +165,15 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
             if (chunk * CCH + cl < c) {
                 const float *frow = fbase + cl * NN * NA;
 #pragma unroll
-                for (int n = 0; n < NN; ++n) {
-                    const float f = (F != nullptr) ? frow[n * NA] : 1.0f;
+                for (int n4 = 0; n4 < NN; n4 += 4) {
+                    if (n4 < nn) {  // CTA-uniform: whole groups of 4 absent neighbours are skipped
 #pragma unroll
-                    for (int i = 0; i < KG; ++i) acc[i] = fmaf(w[i][n], f, acc[i]);
+                        for (int n = n4; n < n4 + 4; ++n) {
+                            const float f = (F != nullptr) ? frow[n * NA] : 1.0f;
+#pragma unroll
+                            for (int i = 0; i < KG; ++i) acc[i] = fmaf(w[i][n], f, acc[i]);
+                        }
+                    }
                 }
             }
             if (a_ok) {
@@ -200,7 +227,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
 template <int NN, int KG, int CCH, int NA>
 static int launch_variant(const float *feats, const int32_t *idx, const InterGeom &g, const TileOut &o, dim3 grid, int c,
                           int p_in, int p, int nn, int p_off, cudaStream_t s) {
-    const size_t smem = (size_t)(NN * 4 + 2 * CCH * NN * NA + CCH * GT_KS * (NA + 1)) * sizeof(float);
+    const size_t smem = (size_t)(NN * 6 + 2 * CCH * NN * NA + CCH * GT_KS * (NA + 1)) * sizeof(float);
     static bool set = false;
     if (!set) {
         cudaFuncSetAttribute(inter_group_tiles_kernel<NN, KG, CCH, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -133,10 +133,13 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
                      InterGeom g, float *__restrict__ dfeats, int c, int p_in, int p, int nn, int p_off) {
     constexpr int NTHR = SC_LANES * (NN / SC_NB);
     extern __shared__ __align__(16) float s_dyn[];
-    float *s_g = s_dyn;                                            // [NN][3]
-    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]
-    float *Ds = s_dyn + NN * 4;                                    // [2][SC_CCH*24][NA]
+    float *s_g = s_dyn;                                            // [NN][3]  distinct neighbour offsets
+    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]     distinct neighbour indices
+    float *s_mult = s_dyn + NN * 4;                                // [NN]     multiplicities
+    int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     ball-query row as stored
+    float *Ds = s_dyn + NN * 6;                                    // [2][SC_CCH*24][NA]
     __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_nu;
     const int tid = threadIdx.x;
     const int a = tid % SC_LANES, grp = tid / SC_LANES;
     const int n0 = grp * SC_NB;
@@ -145,19 +148,33 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
     float *DF = dfeats + (size_t)z * c * p_in * NA;
 
-    for (int n = tid; n < NN; n += NTHR) {
-        int q = 0;
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-        if (n < nn) {
-            q = idx[((size_t)z * p + pi) * nn + n];
+    // distinct neighbours + multiplicities (see inter_group_tiles_kernel): one RED per distinct neighbour
+    for (int n = tid; n < NN; n += NTHR) s_raw[n] = n < nn ? idx[((size_t)z * p + pi) * nn + n] : -1;
+    __syncthreads();
+    if (tid < 32) {
+        const int n = tid;
+        const int q = n < nn ? s_raw[n] : -1;
+        bool uniq = n < nn;
+        for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
+        int mult = 0;
+        for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, uniq);
+        const int pos = __popc(mask & ((1u << n) - 1u));
+        if (uniq) {
             const float *X = g.xyz + (size_t)z * 3 * p_in;
             const float *Cn = g.centers + (size_t)z * 3 * p;
-            gx = X[q] - Cn[pi];
-            gy = X[p_in + q] - Cn[p + pi];
-            gz = X[2 * p_in + q] - Cn[2 * p + pi];
+            s_idx[pos] = q;
+            s_mult[pos] = (float)mult;
+            s_g[pos * 3] = X[q] - Cn[pi];
+            s_g[pos * 3 + 1] = X[p_in + q] - Cn[p + pi];
+            s_g[pos * 3 + 2] = X[2 * p_in + q] - Cn[2 * p + pi];
         }
-        s_idx[n] = q;
-        s_g[n * 3] = gx; s_g[n * 3 + 1] = gy; s_g[n * 3 + 2] = gz;
+        const int cnt = __popc(mask);
+        if (n >= cnt && n < NN) {
+            s_idx[n] = 0; s_mult[n] = 0.f;
+            s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
+        }
+        if (n == 0) s_nu = cnt;
     }
     const uint32_t bar0 = smem_u32(&s_bar[0]);
     if (tid == 0) {
@@ -166,6 +183,8 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
         fence_barrier_init();
     }
     __syncthreads();
+    nn = s_nu;  // number of DISTINCT neighbours
+    const bool grp_active = n0 < nn;  // warp-uniform: this thread's 4 neighbours exist
 
     float w[SC_KS][SC_NB];
     {
@@ -181,7 +200,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
             for (int j = 0; j < SC_NB; ++j) {
                 const int n = n0 + j;
                 const float v = kernel_weight(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, g.sigma);
-                w[k][j] = (a_ok && n < nn) ? v : 0.f;
+                w[k][j] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
             }
         }
     }
@@ -215,7 +234,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
 #pragma unroll 2
         for (int cl = 0; cl < SC_CCH; ++cl) {
             const int cc = chunk * SC_CCH + cl;
-            if (cc >= c) break;
+            if (cc >= c || !grp_active) break;  // idle neighbour groups only keep the barriers company
             float t[SC_NB];
 #pragma unroll
             for (int j = 0; j < SC_NB; ++j) t[j] = 0.f;
@@ -251,11 +270,11 @@ int launch_inter_scatter(const float *dG, long long stride_b, long long stride_c
         set = true;
     }
     if (nn <= 16) {
-        const size_t smem = (size_t)(16 * 4 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(16 * 6 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<16, 60><<<grid, SC_LANES * (16 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     } else {
-        const size_t smem = (size_t)(32 * 4 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(32 * 6 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<32, 60><<<grid, SC_LANES * (32 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     }
