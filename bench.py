@@ -292,7 +292,16 @@ def main():
     else:
         ach = nbytes / t_dom / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak}
-    roof.update({"traffic": None, "kernel": dom, "launches_per_step": kernel_n[dom], "ms_per_step": kernel_ms[dom],
+    traffic = None
+    try:  # measured DRAM bytes of that kernel class from the committed ncu pass of the same step
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_step.json")))["classes"][dom]
+        traffic = tr["dram_bytes"] / max(tr["launches"], 1)
+    except (OSError, KeyError, ValueError):
+        pass
+    per_launch = max(kernel_n[dom], 1)
+    roof["per_launch"] = {"algorithmic": (flops if dom == "channel_gemm" else nbytes) / per_launch,
+                          "avg_ms": kernel_ms[dom] / per_launch, "traffic_bytes": traffic}
+    roof.update({"traffic": traffic, "kernel": dom, "launches_per_step": kernel_n[dom], "ms_per_step": kernel_ms[dom],
                  "share_of_step": kernel_ms[dom] / (ms / args.steps), "peak_source": peak_src,
                  "note": "algorithmic fp32 flops vs the measured sustained bf16 cuBLAS rate (kernel timed inside a long step)"
                  if dom == "channel_gemm" else "grouping-stage bytes of SURVEY.md 8(d)"})
