@@ -11,6 +11,48 @@ import torch.nn.functional as F
 
 from . import functional as L
 from . import modules as sptk
+from . import ops
+
+
+class _NormActFn(torch.autograd.Function):
+    """leaky_relu(norm(x)) as one library op (epn_norm_act_*); saves x and the (mean, rstd) statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mode, eps, slope):
+        x = x.contiguous()
+        y, stats = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope)
+        ctx.save_for_backward(x, stats, gamma, beta)
+        ctx.mode, ctx.slope = mode, slope
+        ctx.mark_non_differentiable(stats)
+        return y, stats
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        x, stats, gamma, beta = ctx.saved_tensors
+        dx, dgamma, dbeta = ops.norm_act_bwd(dy.contiguous(), x, gamma, beta, stats, ctx.mode, ctx.slope)
+        return dx, dgamma, dbeta, None, None, None
+
+
+def norm_act(norm, x, act):
+    """`act(norm(x))` of the block wrappers (base_so3conv.py:55-57,119-125,209).  The two combinations every
+    shipped model uses on CUDA -- InstanceNorm2d(affine=False) / training-mode BatchNorm2d followed by
+    leaky_relu -- run as one fused library op; anything else goes through the torch modules."""
+    fusable = x.is_cuda and x.dtype == torch.float32 and act is F.leaky_relu and x.dim() == 4
+    if fusable and isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats:
+        return _NormActFn.apply(x, None, None, 0, norm.eps, 0.01)[0]
+    if fusable and isinstance(norm, nn.BatchNorm2d) and norm.training and norm.affine:
+        y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, 0.01)
+        if norm.track_running_stats:  # same bookkeeping as nn.BatchNorm2d.forward
+            with torch.no_grad():
+                count = x.numel() // x.shape[1]
+                norm.num_batches_tracked += 1
+                m = norm.momentum if norm.momentum is not None else 1.0 / float(norm.num_batches_tracked)
+                var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))
+                norm.running_mean.mul_(1 - m).add_(stats[0], alpha=m)
+                norm.running_var.mul_(1 - m).add_(var, alpha=m)
+        return y
+    out = norm(x)
+    return act(out) if act is not None else out
 
 
 def preprocess_input(x, na, add_center=True):
@@ -41,9 +83,7 @@ class IntraSO3ConvBlock(nn.Module):
 
     def forward(self, x):
         x = self.conv(x)
-        feat = self.norm(x.feats)
-        if self.relu is not None:
-            feat = self.relu(feat)
+        feat = norm_act(self.norm, x.feats, self.relu)
         if self.training and self.dropout is not None:
             feat = self.dropout(feat)
         return sptk.SphericalPointCloud(x.xyz, feat, x.anchors)
@@ -68,9 +108,7 @@ class InterSO3ConvBlock(nn.Module):
 
     def forward(self, x, inter_idx=None, inter_w=None):
         inter_idx, inter_w, sample_idx, x = self.conv(x, inter_idx, inter_w)
-        feat = self.norm(x.feats)
-        if self.relu is not None:
-            feat = self.relu(feat)
+        feat = norm_act(self.norm, x.feats, self.relu)
         if self.training and self.dropout is not None:
             feat = self.dropout(feat)
         return inter_idx, inter_w, sample_idx, sptk.SphericalPointCloud(x.xyz, feat, x.anchors)
@@ -106,7 +144,7 @@ class SeparableSO3ConvBlock(nn.Module):
         # channel GEMM (cuDNN would silently use TF32), parameters stay in nn.Conv2d for checkpoint parity
         w = self.skip_conv.weight.view(self.skip_conv.out_channels, self.skip_conv.in_channels)
         skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w) + self.skip_conv.bias.view(1, -1, 1, 1)
-        skip_feature = self.relu(self.norm(skip_feature))
+        skip_feature = norm_act(self.norm, skip_feature, self.relu)
         x_out = sptk.SphericalPointCloud(x.xyz, x.feats + skip_feature, x.anchors)
         return inter_idx, inter_w, sample_idx, x_out
 

@@ -32,7 +32,8 @@ enum KernelClass {
     KC_GEMM = 4,         // channel GEMMs (fwd, dX, dW)
     KC_OTHER = 5,
     KC_SPLIT = 5,        // fp32 -> bf16 hi/lo split-tile conversion passes
-    KC_COUNT = 6
+    KC_NORM = 6,         // fused normalisation + leaky_relu
+    KC_COUNT = 7
 };
 
 // RAII: brackets the launches issued in its scope with a cudaEvent pair when profiling is on.

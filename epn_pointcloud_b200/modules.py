@@ -227,8 +227,11 @@ class IntraSO3Conv(nn.Module):
         self.register_buffer("intra_idx", torch.from_numpy(intra_idx).long())
         self.register_buffer("_intra_idx32", torch.from_numpy(intra_idx).int().contiguous(), persistent=False)
         # the int32 copy the kernels read follows `intra_idx` when a checkpoint overwrites it
-        self.register_load_state_dict_post_hook(
-            lambda module, incompatible: module._intra_idx32.copy_(module.intra_idx.to(torch.int32)))
+        self.register_load_state_dict_post_hook(IntraSO3Conv._sync_idx32)
+
+    @staticmethod
+    def _sync_idx32(module, incompatible_keys):
+        module._intra_idx32.copy_(module.intra_idx.to(torch.int32))
 
     def forward(self, x):
         feats = _IntraSO3ConvFn.apply(x.feats, self.basic_conv.W, self._intra_idx32)

@@ -352,6 +352,40 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True)
     return dfeats, dW
 
 
+def norm_act_fwd(x, gamma, beta, mode, eps, slope):
+    """x [b,c,p,a] -> (y, stats[2,G]); mode 0 = InstanceNorm2d(affine=False), 1 = BatchNorm2d (batch statistics),
+    followed by leaky_relu(slope)  (SPConvNets/utils/base_so3conv.py:43,55-57,107,119-125)."""
+    _require_cuda(x, gamma, beta)
+    b, c = x.shape[0], x.shape[1]
+    n = x[0, 0].numel()
+    y = torch.empty_like(x)
+    stats = torch.empty(2, b * c if mode == 0 else c, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        wsb = L.epn_norm_act_workspace_bytes(b, c)
+        ws = _workspace(wsb, x.device)
+        _lib.check(L.epn_norm_act_fwd_f32(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), _p(ws), wsb, b, c, n, int(mode),
+                                          float(eps), float(slope), _stream()), "epn_norm_act_fwd_f32")
+    return y, stats
+
+
+def norm_act_bwd(dy, x, gamma, beta, stats, mode, slope, need_affine_grads=True):
+    _require_cuda(dy, x, gamma, beta, stats)
+    b, c = x.shape[0], x.shape[1]
+    n = x[0, 0].numel()
+    dx = torch.empty_like(x)
+    dgamma = dbeta = None
+    if mode == 1 and gamma is not None and need_affine_grads:
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(gamma)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        wsb = L.epn_norm_act_workspace_bytes(b, c)
+        ws = _workspace(wsb, x.device)
+        _lib.check(L.epn_norm_act_bwd_f32(_p(dy), _p(x), _p(gamma), _p(beta), _p(stats), _p(dx), _p(dgamma), _p(dbeta),
+                                          _p(ws), wsb, b, c, n, int(mode), float(slope), _stream()), "epn_norm_act_bwd_f32")
+    return dx, dgamma, dbeta
+
+
 def set_gemm_backend(name):
     """'umma' (tcgen05 tensor cores, default) or 'simt' (fp32 cross-check path)."""
     _lib.lib().epn_set_gemm_backend({"umma": 0, "simt": 1}[name])

@@ -176,6 +176,22 @@ int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, fl
                            void *workspace, size_t workspace_bytes, int b, int ck, int co, int pa,
                            void *stream);
 
+/* ------------------------------------------------ fused norm + activation (block wrappers)
+ * y = leaky_relu(norm(x) * gamma + beta, slope) on x [b, c, n] (n = points*anchors):
+ *   mode 0: InstanceNorm2d(affine=False) -> leaky_relu  (SPConvNets/utils/base_so3conv.py:43,55-57)
+ *   mode 1: BatchNorm2d, batch statistics, affine -> leaky_relu  (base_so3conv.py:107,119-125,193,209)
+ * gamma/beta [c] may be NULL (= 1 / 0).  stats [2*G] receives (mean, rstd) per group, G = b*c (mode 0)
+ * or c (mode 1); the backward needs it, and the caller derives BatchNorm's running statistics from it.
+ * Backward writes dx fully and, for mode 1, dgamma/dbeta [c] (NULL to skip).
+ * workspace: epn_norm_act_workspace_bytes(b, c) bytes. */
+size_t epn_norm_act_workspace_bytes(int b, int c);
+int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, float *y, float *stats,
+                         void *workspace, size_t workspace_bytes, int b, int c, int n, int mode, float eps,
+                         float slope, void *stream);
+int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *gamma, const float *beta,
+                         const float *stats, float *dx, float *dgamma, float *dbeta, void *workspace,
+                         size_t workspace_bytes, int b, int c, int n, int mode, float slope, void *stream);
+
 /* Channel-GEMM engine used by the three convs: 0 = tcgen05 tensor cores with bf16 hi/lo
  * operand splitting (default; fp32-faithful to ~1e-5 relative), 1 = fp32 SIMT GEMM (the
  * in-library cross-check used by the GPU tests; also selectable with EPN_GEMM=simt). */

@@ -511,3 +511,38 @@ def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, r
     assert rel_err(conv.basic_conv.W.grad, W.grad) < FEAT_TOL
     if c_in != 1:
         assert rel_err(fg.grad, fc.grad) < FEAT_TOL
+
+
+# ------------------------------------------------- fused norm + leaky_relu of the block wrappers (8 f1)
+@pytest.mark.parametrize("b,c,p,a", [(2, 8, 32, 60), (4, 64, 128, 60), (3, 5, 7, 20), (1, 16, 50, 1)])
+def test_fused_norm_act_vs_torch_fp64(E, b, c, p, a):
+    """BatchNorm2d(train)+leaky_relu and InstanceNorm2d+leaky_relu as one library op vs torch in float64,
+    forward, dx, dgamma, dbeta and the running-statistics bookkeeping (base_so3conv.py:43,55-57,107,119-125)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from epn_pointcloud_b200.blocks import norm_act
+    gen = torch.Generator().manual_seed(b * 100 + c)
+    x0 = (torch.randn(b, c, p, a, generator=gen) * 3.0 + 5.0)   # large mean: exercises the variance computation
+    r = torch.randn(b, c, p, a, generator=gen)
+    for kind in ("batch", "instance"):
+        if kind == "batch":
+            mine, ref = nn.BatchNorm2d(c).to(DEV).train(), nn.BatchNorm2d(c).double().train()
+            with torch.no_grad():
+                mine.weight.copy_(torch.rand(c, generator=gen) + 0.5)
+                mine.bias.copy_(torch.randn(c, generator=gen))
+                ref.weight.copy_(mine.weight.double().cpu())
+                ref.bias.copy_(mine.bias.double().cpu())
+        else:
+            mine, ref = nn.InstanceNorm2d(c, affine=False).to(DEV), nn.InstanceNorm2d(c, affine=False).double()
+        xg = x0.to(DEV).requires_grad_(True)
+        xr = x0.double().requires_grad_(True)
+        y = norm_act(mine, xg, F.leaky_relu)
+        yr = F.leaky_relu(ref(xr))
+        assert rel_err(y, yr) < 1e-5
+        (y * r.to(DEV)).sum().backward()
+        (yr * r.double()).sum().backward()
+        assert rel_err(xg.grad, xr.grad) < 1e-4
+        if kind == "batch":
+            assert rel_err(mine.weight.grad, ref.weight.grad) < 1e-4 and rel_err(mine.bias.grad, ref.bias.grad) < 1e-4
+            assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-4
+            assert int(mine.num_batches_tracked) == 1
