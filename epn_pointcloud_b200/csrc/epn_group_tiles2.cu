@@ -138,7 +138,6 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     float *s_mult = s_dyn + NN * 4;                                // [NN]     multiplicities
     int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     ball-query row as stored
     float *Ds = s_dyn + NN * 6;                                    // [2][SC_CCH*24][NA]
-    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_nu;
     const int tid = threadIdx.x;
     const int a = tid % SC_LANES, grp = tid / SC_LANES;
@@ -176,12 +175,6 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
         }
         if (n == 0) s_nu = cnt;
     }
-    const uint32_t bar0 = smem_u32(&s_bar[0]);
-    if (tid == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8u, 1);
-        fence_barrier_init();
-    }
     __syncthreads();
     nn = s_nu;  // number of DISTINCT neighbours
     const bool grp_active = n0 < nn;  // warp-uniform: this thread's 4 neighbours exist
@@ -211,25 +204,32 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     const size_t cplane = (size_t)p_in * NA;
 
     const int nchunks = (c + SC_CCH - 1) / SC_CCH;
+    // staged gradient rows: 16-byte cp.async (LDGSTS) pieces, 15 per 240-byte row (one UBLKCP per row was
+    // measured TMA-issue-bound at this size)
+    constexpr int SEGS = NA / 4;
     const uint32_t ds_u32 = smem_u32(Ds);
-    constexpr uint32_t ROW_BYTES = NA * 4;
     const float *src0 = dG + (size_t)z * stride_b + (size_t)pl * NA;
     auto issue = [&](int chunk, int buf) {
         const int rows = min(SC_CCH, c - chunk * SC_CCH) * SC_KS;
-        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
-        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)rows * ROW_BYTES);
-        for (int rr = tid; rr < rows; rr += NTHR)  // rr = cl*24 + k
-            bulk_g2s(ds_u32 + (uint32_t)((buf * SC_CCH * SC_KS + rr) * NA) * 4u,
-                     src0 + (size_t)(chunk * SC_CCH * SC_KS + rr) * stride_ck, ROW_BYTES, bar);
+        for (int t = tid; t < rows * SEGS; t += NTHR) {
+            const int rr = t / SEGS, seg = t - rr * SEGS;  // rr = cl*24 + k
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         ::"r"(ds_u32 + (uint32_t)(((buf * SC_CCH * SC_KS + rr) * NA + seg * 4) * 4)),
+                           "l"(src0 + (size_t)(chunk * SC_CCH * SC_KS + rr) * stride_ck + seg * 4) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
-    uint32_t phase_bits = 0u;
     issue(0, 0);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int buf = chunk & 1;
-        if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
-        mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
-        phase_bits ^= 1u << buf;
+        if (chunk + 1 < nchunks) {
+            issue(chunk + 1, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();  // rows of this chunk visible to every thread
         const float *dbase = Ds + (size_t)(buf * SC_CCH * SC_KS) * NA + aa;
 #pragma unroll 2
         for (int cl = 0; cl < SC_CCH; ++cl) {

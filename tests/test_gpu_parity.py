@@ -541,7 +541,12 @@ def test_fused_norm_act_vs_torch_fp64(E, b, c, p, a):
         assert rel_err(y, yr) < 1e-5
         (y * r.to(DEV)).sum().backward()
         (yr * r.double()).sum().backward()
-        assert rel_err(xg.grad, xr.grad) < 1e-4
+        # leaky_relu has a kink at 0: an element whose pre-activation is within fp32 rounding of 0 may take the
+        # other slope than the float64 evaluation; such elements (|z| < 1e-5 max|z|) are left out of the check
+        z = ref(xr).detach()
+        keep = (z.abs() > 1e-5 * z.abs().max()).to(DEV)
+        assert float(keep.float().mean()) > 0.999
+        assert rel_err(xg.grad * keep, xr.grad * keep.cpu()) < 1e-4
         if kind == "batch":
             assert rel_err(mine.weight.grad, ref.weight.grad) < 1e-4 and rel_err(mine.bias.grad, ref.bias.grad) < 1e-4
             assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-4
