@@ -5,9 +5,9 @@
 //
 // One CTA per output point.  lane <-> anchor a (feature rows [c, q, 0..na) are contiguous 4*na-byte
 // segments), warp-pair <-> group of KG kernel points; a thread keeps its w[KG][NN] slice of the kernel
-// weights in registers for the whole point.  Channels stream through in chunks of CCH: the neighbour
-// feature rows of a chunk are fetched with 16-byte cp.async (LDGSTS) pieces into a double-buffered stage
-// (the gather of chunk i+1 overlaps the FMAs of chunk i), the
+// weights in registers for the whole point.  Channels stream through in chunks of CCH: every neighbour
+// feature row of a chunk is fetched with ONE bulk async copy (UBLKCP, 4*na bytes) that completes on the
+// stage buffer's mbarrier (double buffered: the gather of chunk i+1 overlaps the FMAs of chunk i), the
 // per-anchor spatial contraction writes fp32 results to a shared staging tile, and a conversion pass
 // splits them into bf16 hi/lo and stores 16-byte (forward layout) or 8-byte (transposed layout) pieces of
 // the canonical UMMA operand tiles (epn_umma.cuh) -- the grouped tensor never exists in fp32 in global
@@ -23,13 +23,6 @@ using namespace umma;
 
 constexpr int GT_LANES = 64;  // anchor lanes per kernel-point group
 constexpr int GT_KS = 24;     // kernel points (kpsphere24)
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 struct TileOut {
     uint8_t *tiles;
@@ -53,6 +46,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     the ball-query row as stored
     float *Fs = s_dyn + NN * 6;                                    // [2][CCH][NN][NA]
     float *Gs = Fs + 2 * CCH * NN * NA;                            // [CKK][GSTR]
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_nu;
     const int tid = threadIdx.x;
     const int a = tid % GT_LANES, grp = tid / GT_LANES;
@@ -93,6 +87,12 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
         }
         if (n == 0) s_nu = cnt;
     }
+    const uint32_t bar0 = smem_u32(&s_bar[0]);  // buffer b uses the barrier at bar0 + 8*b
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_barrier_init();
+    }
     __syncthreads();
     nn = s_nu;  // from here on: number of DISTINCT neighbours
     // rows beyond the distinct neighbours are never copied: keep them zero in both buffers (the FMA loop runs
@@ -124,22 +124,18 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
 
     const int nchunks = (c + CCH - 1) / CCH;
     const uint32_t fs_u32 = smem_u32(Fs);
-    // Gather: 16-byte cp.async (LDGSTS) pieces, 15 per 240-byte neighbour row.  (One bulk copy per row was
-    // measured TMA-issue-bound: ~50 cycles per 240-byte UBLKCP caps an SM at ~5 B/cycle.)
-    constexpr int SEGS = NA / 4;
+    constexpr uint32_t ROW_BYTES = NA * 4;
     auto issue = [&](int chunk, int buf) {
-        if (F != nullptr) {
-            const int nch = min(CCH, c - chunk * CCH);
-            for (int cl = 0; cl < nch; ++cl) {
-                const float *src_c = F + (size_t)(chunk * CCH + cl) * p_in * NA;
-                const uint32_t dst_c = fs_u32 + (uint32_t)((buf * CCH + cl) * NN * NA) * 4u;
-                for (int t = tid; t < nn * SEGS; t += NTHR) {
-                    const int n = t / SEGS, seg = t - n * SEGS;
-                    cp_async16(dst_c + (uint32_t)(n * NA + seg * 4) * 4u, src_c + (size_t)s_idx[n] * NA + seg * 4);
-                }
-            }
+        if (F == nullptr) return;
+        const int nch = min(CCH, c - chunk * CCH);
+        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nch * nn) * ROW_BYTES);
+        for (int t = tid; t < nch * NN; t += NTHR) {
+            const int cl = t / NN, n = t % NN;
+            if (n < nn)
+                bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
+                         F + ((size_t)(chunk * CCH + cl) * p_in + s_idx[n]) * NA, ROW_BYTES, bar);
         }
-        cp_async_commit();
     };
 
     // conversion addressing that does not depend on the chunk
@@ -147,16 +143,16 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     const long long row_m0 = col0 + aa;  // mode 0: this thread's tile row
     uint8_t *m0_base = out.tiles + ((size_t)(row_m0 >> 7) * out.k_blocks) * tile_bytes(TR_A) + (size_t)(row_m0 & 127) * 16;
 
+    uint32_t phase_bits = 0u;  // bit b = parity to wait for on buffer b
     issue(0, 0);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int buf = chunk & 1;
-        if (chunk + 1 < nchunks) {
-            issue(chunk + 1, buf ^ 1);  // overlaps the FMAs / conversion of this chunk
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
+        if (F != nullptr) {
+            mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
+            phase_bits ^= 1u << buf;
         }
-        __syncthreads();  // this chunk's rows have landed for every thread; previous conversion finished reading Gs
+        __syncthreads();  // previous conversion finished reading Gs
 
         // ---- spatial contraction of CCH channels: 1 LDS + KG FFMA per neighbour, KG STS per channel
         const float *fbase = Fs + (size_t)(buf * CCH * NN) * NA + aa;
