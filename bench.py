@@ -116,18 +116,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_port_step(layers, x, requires_grad=True):
-    """One fwd+bwd of the backbone through oracle/torch_port.py (the reference's op chain on CPU)."""
+def synthetic_labels(b, seed):
+    return torch.randint(0, 40, (b,), generator=torch.Generator().manual_seed(1000 + seed))
+
+
+def cpu_port_step(port, x, labels, requires_grad=True):
+    """One fwd+bwd of the classification network (backbone + head + cross-entropy) through
+    oracle/torch_port.py (the reference's op chain on CPU)."""
     from oracle import torch_port as TP
-    leaves = []
+    layers, hp = port
     for prm, *_ in layers:
         for k in prm:
             prm[k] = prm[k].detach().requires_grad_(requires_grad)
-            leaves.append(prm[k])
-    _, feats = TP.backbone_forward(x, layers)
-    loss = feats.square().mean()
+    for k, v in hp.items():
+        if k != "anchors":
+            hp[k] = [t.detach().requires_grad_(requires_grad) for t in v] if isinstance(v, list) else \
+                v.detach().requires_grad_(requires_grad)
+    xyz, feats = TP.backbone_forward(x, layers)
+    logits, _ = TP.cls_head(xyz, feats, hp)
+    loss = torch.nn.functional.cross_entropy(logits, labels)
     loss.backward()
     return float(loss.detach())
+
+
+def port_of(model):
+    from oracle import torch_port as TP
+    return TP.layers_from_module(model), TP.head_from_module(model.outblock)
 
 
 def run_reference(args, rank):
@@ -135,26 +149,26 @@ def run_reference(args, rank):
     reference is Python and cannot travel to the GPU box) on all host cores."""
     if rank != 0:
         return
-    from epn_pointcloud_b200.blocks import SO3ConvBackbone, cls_backbone_params
-    from oracle import torch_port as TP
+    from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    model = SO3ConvBackbone(cls_backbone_params(N_POINTS, N_ANCHORS), N_ANCHORS)
-    layers = TP.layers_from_module(model)
+    model = ClsSO3ConvModel(cls_model_params(N_POINTS, N_ANCHORS))
+    port = port_of(model)
     sample = args.ref_batch
-    x = synthetic_clouds(sample, N_POINTS, 2)
+    x, labels = synthetic_clouds(sample, N_POINTS, 2), synthetic_labels(sample, 2)
     for _ in range(args.warmup):
-        cpu_port_step(layers, x)
+        cpu_port_step(port, x, labels)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_port_step(layers, x)
+        cpu_port_step(port, x, labels)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cls backbone fwd+bwd, 1024 pts, 60 anchors (BASELINE configs[1])",
+            "config": {"workload": "ModelNet40 cls network (7 inter + 7 intra SPConv layers + head) fwd+bwd, 1024 pts, "
+                                   "60 anchors (BASELINE configs[1])",
                        "sample": "%d clouds per step (bounded sample of the 32-cloud batch)" % sample},
             "cpu_baseline": {"value": value, "unit": "clouds/s", "cores": cores, "kind": "port",
                              "sample": "%d clouds/step x %d steps, oracle/torch_port.py (reference op chain, torch CPU)" % (sample, args.steps)},
@@ -186,7 +200,7 @@ def main():
     import torch.distributed as dist
     import epn_pointcloud_b200  # noqa: F401
     from epn_pointcloud_b200 import _lib
-    from epn_pointcloud_b200.blocks import SO3ConvBackbone, cls_backbone_params
+    from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
     from epn_pointcloud_b200.parallel import FlatGradSync
 
     assert torch.cuda.is_available(), "bench.py measures the CUDA path; there is no CPU fallback"
@@ -199,18 +213,19 @@ def main():
     assert L.epn_device_supported() == 1
 
     torch.manual_seed(0)  # identical weights on every rank
-    model = SO3ConvBackbone(cls_backbone_params(N_POINTS, N_ANCHORS), N_ANCHORS).to(dev).train()
+    model = ClsSO3ConvModel(cls_model_params(N_POINTS, N_ANCHORS)).to(dev).train()
     sync = FlatGradSync(model.parameters())
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     B = args.batch
     x_host = synthetic_clouds(B, N_POINTS, 2 + rank).pin_memory()
     x_dev = x_host.to(dev)
     x_stage = torch.empty_like(x_dev)
+    labels = synthetic_labels(B, 2 + rank).to(dev)
 
     def step(x):
         sync.zero()
-        y = model(x)
-        loss = y.feats.square().mean()
+        logits, _ = model(x)
+        loss = torch.nn.functional.cross_entropy(logits, labels)
         loss.backward()
         sync.all_reduce_mean()
         opt.step()
@@ -310,8 +325,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": "clouds/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cls backbone fwd+bwd+Adam, 1024 pts, 60 anchors, 7 inter + 7 intra layers "
-                                   "(BASELINE configs[1])", "clouds_per_gpu": B, "global_batch": B * world,
+            "config": {"workload": "ModelNet40 cls network (7 inter + 7 intra SPConv layers + head) fwd+bwd+Adam, "
+                                   "1024 pts, 60 anchors (BASELINE configs[1])", "clouds_per_gpu": B, "global_batch": B * world,
                        "parallelism": "batch-sharded x%d, one flat-gradient all-reduce" % world,
                        "l2": "no explicit flush: every step streams several GB of activations through the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "clouds/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
@@ -323,10 +338,10 @@ def main():
         from oracle import torch_port as TP
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        layers = TP.layers_from_module(model)
-        xs = synthetic_clouds(args.ref_batch, N_POINTS, 2)
+        port = port_of(model)
+        xs, ls = synthetic_clouds(args.ref_batch, N_POINTS, 2), synthetic_labels(args.ref_batch, 2)
         t0 = time.perf_counter()
-        cpu_port_step(layers, xs)
+        cpu_port_step(port, xs, ls)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": args.ref_batch / dt, "unit": "clouds/s", "cores": cores, "kind": "port",
                                 "sample": "%d clouds, 1 fwd+bwd step of the same backbone through oracle/torch_port.py "

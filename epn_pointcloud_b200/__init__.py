@@ -11,7 +11,7 @@ The compute path has no CPU / PyTorch fallback: importing is cheap, but the firs
 raises if libepn_b200.so is missing (build it with `__graft_entry__.build()`).
 """
 from . import _lib  # noqa: F401
-from . import ops, functional, modules, blocks  # noqa: F401
+from . import ops, functional, modules, blocks, heads  # noqa: F401
 from .modules import BasicSO3Conv, InterSO3Conv, IntraSO3Conv, SphericalPointCloud  # noqa: F401
 
 __version__ = "0.1.0"

@@ -159,6 +159,20 @@ def main():
     save("backbone_small", pc=npy(pc), out=npy(x.feats), out_xyz=npy(x.xyz), r=npy(r),
          params=np.array(json.dumps(bp)), **sd0, **grads)
 
+    # ---- classification head (ClsOutBlockPointnet + PointnetSO3Conv), training mode
+    torch.manual_seed(8)
+    hp = {"dim_in": 16, "mlp": [24], "fc": [64], "k": 40, "pooling": "max", "temperature": 3.0, "kanchor": 60}
+    head = M.ClsOutBlockPointnet(dict(hp)).train()
+    pc = sphere_points(3, 32, 8)
+    feats = torch.randn(3, 16, 32, 60, generator=torch.Generator().manual_seed(24)).requires_grad_(True)
+    sd0 = sd_arrays(head)
+    logits, hfeat = head(zptk.SphericalPointCloud(pc.permute(0, 2, 1).contiguous(), feats, None))
+    r = torch.randn(logits.shape, generator=torch.Generator().manual_seed(25))
+    (logits * r).sum().backward()
+    grads = {"grad." + k: npy(p.grad) for k, p in head.named_parameters()}
+    save("cls_head", pc=npy(pc), feats=npy(feats), logits=npy(logits), hfeat=npy(hfeat), r=npy(r),
+         dfeats=npy(feats.grad), params=np.array(json.dumps(hp)), **sd0, **grads)
+
     # ---- the reference's own layer arithmetic for the three shipped models at the BASELINE sizes
     def opt_for(input_num, kanchor=60):
         o = types.SimpleNamespace()
@@ -180,6 +194,8 @@ def main():
         out[name] = json.load(open(path))["backbone"]
         out[name + "_n_params"] = sum(p.numel() for p in model.parameters())
         out[name + "_state_keys"] = sorted(k for k in model.state_dict().keys() if k.startswith("backbone."))
+        out[name + "_state_shapes_all"] = {k: list(v.shape) for k, v in model.state_dict().items()}
+        out[name + "_outblock"] = json.load(open(path))["outblock"]
         os.remove(path)
     json.dump(out, open(os.path.join(OUT, "model_params.json"), "w"), indent=0)
     print("wrote model_params.json", out["cls_n_params"])

@@ -134,6 +134,32 @@ def backbone_forward(x, layers, dtype=torch.float32):
     return xyz, feats
 
 
+def cls_head(xyz, feats, hp):
+    """ClsOutBlockPointnet.forward with 'max' pooling, training mode (SPConvNets/utils/base_so3conv.py:404-448)
+    incl. PointnetSO3Conv (vgtk/vgtk/so3conv/modules.py:218-235).  hp: dict of tensors
+    {lin_w[i], lin_b[i], bn_w[i], bn_b[i] (lists), pn_w, pn_b, bn1_w, bn1_b, fc_w, fc_b, anchors}."""
+    x = feats
+    for w, b, gw, gb in zip(hp["lin_w"], hp["lin_b"], hp["bn_w"], hp["bn_b"]):
+        x = F.relu(F.batch_norm(F.conv2d(x, w, b), None, None, gw, gb, True, 0.1, 1e-5))
+    out_feat = x
+    c = xyz - xyz.mean(2, keepdim=True)
+    xyzr = torch.einsum("aji,bjn->bina", hp["anchors"].to(x.dtype), c.to(x.dtype))
+    x = F.conv2d(torch.cat([x, xyzr], 1), hp["pn_w"], hp["pn_b"]).max(2)[0]
+    x = F.relu(F.batch_norm(x, None, None, hp["bn1_w"], hp["bn1_b"], True, 0.1, 1e-5))
+    return F.linear(x.max(2)[0], hp["fc_w"], hp["fc_b"]), out_feat
+
+
+def head_from_module(outblock):
+    """Tensors of an `epn_pointcloud_b200.heads.ClsOutBlockPointnet` (or the reference's) for cls_head()."""
+    sd = {k: v.detach().cpu().float() for k, v in outblock.state_dict().items()}
+    n = len(outblock.linear)
+    return {"lin_w": [sd["linear.%d.weight" % i] for i in range(n)], "lin_b": [sd["linear.%d.bias" % i] for i in range(n)],
+            "bn_w": [sd["norm.%d.weight" % i] for i in range(n)], "bn_b": [sd["norm.%d.bias" % i] for i in range(n)],
+            "pn_w": sd["pointnet.embed.weight"], "pn_b": sd["pointnet.embed.bias"], "anchors": sd["pointnet.anchors"],
+            "bn1_w": sd["norm.%d.weight" % n], "bn1_b": sd["norm.%d.bias" % n], "fc_w": sd["fc2.weight"],
+            "fc_b": sd["fc2.bias"]}
+
+
 def layers_from_module(backbone):
     """Pull (prm, args, ...) out of an `epn_pointcloud_b200.blocks.SO3ConvBackbone` (or the
     reference's ModuleList of BasicSO3ConvBlock) living on any device -> CPU tensors."""

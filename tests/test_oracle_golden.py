@@ -59,6 +59,29 @@ def test_model_param_arithmetic_and_state_keys():
     assert sorted(model.state_dict().keys()) == ref["cls_state_keys"]
 
 
+def test_full_cls_model_matches_reference_structure():
+    """ClsSO3ConvModel (backbone + ClsOutBlockPointnet head): same parameter/buffer names, shapes and count
+    as the reference's build_model output (7,814,632 parameters), so its checkpoints load key for key."""
+    from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
+    ref = json.load(open(os.path.join(GOLDEN, "model_params.json")))
+    params = json.loads(json.dumps(cls_model_params(1024, 60)))
+    assert params["outblock"] == ref["cls_outblock"] and params["backbone"] == ref["cls"]
+    model = ClsSO3ConvModel(cls_model_params(1024, 60))
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == ref["cls_state_shapes_all"]
+    assert sum(p.numel() for p in model.parameters()) == ref["cls_n_params"]
+
+
+def test_cls_head_port():
+    from epn_pointcloud_b200.heads import ClsOutBlockPointnet
+    g = load_golden("cls_head")
+    head = ClsOutBlockPointnet(dict(g["params"]))
+    head.load_state_dict(g.state_dict(), strict=True)
+    hp = TP.head_from_module(head)
+    logits, hfeat = TP.cls_head(g["pc"].permute(0, 2, 1).contiguous(), g["feats"], hp)
+    assert rel_err(logits, g["logits"]) < TOL and rel_err(hfeat, g["hfeat"]) < TOL
+
+
 def test_inter_a20_occupancy():
     g = load_golden("inter_a20_occupancy")
     sd = g.state_dict()
