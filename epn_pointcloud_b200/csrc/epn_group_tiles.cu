@@ -32,7 +32,7 @@ struct TileOut {
     int mode;
 };
 
-template <int NN, int KG, int CCH, int NA>
+template <int NN, int KG, int CCH, int NA, bool HAS_FEATS>
 __global__ void __launch_bounds__(GT_LANES *(GT_KS / KG), NN == 16 ? 2 : 1)
 inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restrict__ idx, InterGeom g, TileOut out,
                          int c, int p_in, int p, int nn, int p_off) {
@@ -116,7 +116,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
                         rz = R[6] * kx + R[7] * ky + R[8] * kz;
 #pragma unroll
             for (int n = 0; n < NN; ++n) {
-                const float v = kernel_weight(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, g.sigma);
+                const float v = kernel_weight_fast(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, 1.0f / g.sigma);
                 w[i][n] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
             }
         }
@@ -126,7 +126,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     const uint32_t fs_u32 = smem_u32(Fs);
     constexpr uint32_t ROW_BYTES = NA * 4;
     auto issue = [&](int chunk, int buf) {
-        if (F == nullptr) return;
+        if (!HAS_FEATS) return;
         const int nch = min(CCH, c - chunk * CCH);
         const uint32_t bar = bar0 + 8u * (uint32_t)buf;
         if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nch * nn) * ROW_BYTES);
@@ -148,7 +148,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     for (int chunk = 0; chunk < nchunks; ++chunk) {
         const int buf = chunk & 1;
         if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
-        if (F != nullptr) {
+        if (HAS_FEATS) {
             mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
             phase_bits ^= 1u << buf;
         }
@@ -169,7 +169,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
                     if (n4 < nn) {  // CTA-uniform: whole groups of 4 absent neighbours are skipped
 #pragma unroll
                         for (int n = n4; n < n4 + 4; ++n) {
-                            const float f = (F != nullptr) ? frow[n * NA] : 1.0f;
+                            const float f = HAS_FEATS ? frow[n * NA] : 1.0f;  // occupancy features == 1
 #pragma unroll
                             for (int i = 0; i < KG; ++i) acc[i] = fmaf(w[i][n], f, acc[i]);
                         }
@@ -224,16 +224,16 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     }
 }
 
-template <int NN, int KG, int CCH, int NA>
+template <int NN, int KG, int CCH, int NA, bool HAS_FEATS>
 static int launch_variant(const float *feats, const int32_t *idx, const InterGeom &g, const TileOut &o, dim3 grid, int c,
                           int p_in, int p, int nn, int p_off, cudaStream_t s) {
     const size_t smem = (size_t)(NN * 6 + 2 * CCH * NN * NA + CCH * GT_KS * (NA + 1)) * sizeof(float);
     static bool set = false;
     if (!set) {
-        cudaFuncSetAttribute(inter_group_tiles_kernel<NN, KG, CCH, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(inter_group_tiles_kernel<NN, KG, CCH, NA, HAS_FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         set = true;
     }
-    inter_group_tiles_kernel<NN, KG, CCH, NA><<<grid, GT_LANES *(GT_KS / KG), smem, s>>>(feats, idx, g, o, c, p_in, p, nn, p_off);
+    inter_group_tiles_kernel<NN, KG, CCH, NA, HAS_FEATS><<<grid, GT_LANES *(GT_KS / KG), smem, s>>>(feats, idx, g, o, c, p_in, p, nn, p_off);
     return check_launch("inter_group_tiles_kernel");
 }
 
@@ -245,8 +245,12 @@ int launch_inter_group_tiles(const float *feats, const int32_t *idx, const Inter
     TileOut o{static_cast<uint8_t *>(tiles), k_blocks, row_limit, cols_per_z, mode};
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_GROUP);
-    if (nn <= 16) return launch_variant<16, 6, 8, 60>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
-    return launch_variant<32, 3, 4, 60>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
+    if (feats == nullptr) {  // occupancy features (layer 0): nothing to gather
+        if (nn <= 16) return launch_variant<16, 6, 8, 60, false>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
+        return launch_variant<32, 3, 4, 60, false>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
+    }
+    if (nn <= 16) return launch_variant<16, 6, 8, 60, true>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
+    return launch_variant<32, 3, 4, 60, true>(feats, idx, g, o, grid, c, p_in, p, nn, p_off, s);
 }
 
 }  // namespace epn

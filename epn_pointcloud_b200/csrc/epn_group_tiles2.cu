@@ -192,7 +192,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
 #pragma unroll
             for (int j = 0; j < SC_NB; ++j) {
                 const int n = n0 + j;
-                const float v = kernel_weight(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, g.sigma);
+                const float v = kernel_weight_fast(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, 1.0f / g.sigma);
                 w[k][j] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
             }
         }
