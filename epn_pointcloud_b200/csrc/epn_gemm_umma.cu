@@ -53,6 +53,48 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
     }
 }
 
+// k-contiguous sources (dout as the dW operand, W): a block converts 32 rows x 64 k.  Loads run along k
+// (8 lanes x 32 B contiguous per row), the hi/lo 16-byte chunks are transposed through shared memory, and
+// the stores run along rows (32 lanes x 16 B = 512 contiguous bytes of the tile) instead of isolated 16-byte
+// pieces.
+__global__ void __launch_bounds__(256)
+split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int k_blocks) {
+    __shared__ uint4 s_hi[8][33], s_lo[8][33];
+    const int tid = threadIdx.x;
+    const int row0 = blockIdx.y * 32, kcg0 = blockIdx.x * 8;
+    {
+        const int r = tid >> 3, kq = tid & 7;
+        const int row = row0 + r, kcg = kcg0 + kq;
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        if (row < rows) {
+            const float *base = src.ptr;
+            if (src.rows_per_z < rows) base += (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
+            else base += (long long)row * src.stride_row;
+            long long kz = 0, kj = (long long)kcg * 8;
+            if (src.k_per_z < K) { kz = kj / src.k_per_z; kj -= kz * src.k_per_z; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (kcg * 8 + i < K) x[i] = __ldg(base + kz * src.stride_kz + kj * src.stride_k);
+                if (++kj == src.k_per_z) { kj = 0; ++kz; }
+            }
+        }
+        split8(x, s_hi[kq][r], s_lo[kq][r]);
+    }
+    __syncthreads();
+    {
+        const int kq = tid >> 5, r = tid & 31;
+        const int row = row0 + r, kcg = kcg0 + kq;
+        if (kcg < k_blocks * (KB / 8) && row < (rows + tr - 1) / tr * tr) {
+            const int rt = row / tr, rr = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
+            uint8_t *tile = dst + ((size_t)rt * k_blocks + kb) * tile_bytes(tr);
+            *reinterpret_cast<uint4 *>(tile + (size_t)kc * tr * 16 + (size_t)rr * 16) = s_hi[kq][r];
+            *reinterpret_cast<uint4 *>(tile + part_bytes(tr) + (size_t)kc * tr * 16 + (size_t)rr * 16) = s_lo[kq][r];
+        }
+    }
+}
+
 size_t split_tiles_bytes(long long rows, long long K, int tr) {
     const long long row_tiles = (rows + tr - 1) / tr, k_blocks = (K + KB - 1) / KB;
     return (size_t)row_tiles * k_blocks * tile_bytes(tr);
@@ -62,7 +104,10 @@ int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long
     const int row_tiles = (int)((rows + tr - 1) / tr), k_blocks = (int)((K + KB - 1) / KB);
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     ProfScope prof(s, KC_SPLIT);
-    if (src.stride_k == 1 && src.stride_row != 1) {
+    if (src.stride_k == 1 && src.stride_row != 1 && (rows_pad + 31) / 32 <= 65535) {
+        dim3 grid((kcgs + 7) / 8, (rows_pad + 31) / 32);
+        split_tiles_kcontig_kernel<<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, k_blocks);
+    } else if (src.stride_k == 1 && src.stride_row != 1) {
         dim3 grid((kcgs + 255) / 256, rows_pad < 65535 ? rows_pad : 65535);
         split_tiles_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
                                                       k_blocks);

@@ -16,7 +16,7 @@ import sys
 CLASS_OF = [("umma_gemm", "channel_gemm"), ("sgemm", "channel_gemm"), ("inter_group_tiles", "inter_group_fwd"),
             ("inter_group_fwd", "inter_group_fwd"), ("inter_scatter", "inter_group_bwd_scatter"),
             ("inter_group_bwd", "inter_group_bwd_scatter"), ("intra_", "intra_group"), ("split_tiles", "split_convert"),
-            ("ball_query", "index_ops"), ("fps_kernel", "index_ops"), ("gather_", "index_ops")]
+            ("norm_", "norm_act"), ("ball_query", "index_ops"), ("fps_kernel", "index_ops"), ("gather_", "index_ops")]
 
 
 def to_base(value, unit):
