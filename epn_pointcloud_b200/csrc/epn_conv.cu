@@ -70,6 +70,25 @@ static SlabPlan plan_slabs(int b, int ck, int p, int na) {
     return s;
 }
 
+// Bytes of the forward operand tiles of ALL slabs of one conv call (what a training forward may keep for the
+// weight gradient); 0 when the shape cannot take that route (SIMT backend, or a slab whose column count is
+// not a multiple of the 128-row tile, where padded rows would hold garbage).
+static size_t grouped_tiles_bytes(int b, int ck, int p, int na) {
+    if (gemm_backend() != 0) return 0;
+    const SlabPlan sp = plan_slabs(b, ck, p, na);
+    size_t total = 0;
+    for (int b0 = 0; b0 < b; b0 += sp.bc) {
+        const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
+        for (int p0 = 0; p0 < p; p0 += sp.pc) {
+            const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
+            const long long n = (long long)bc * pc * na;
+            if (n % 128 != 0) return 0;
+            total += split_tiles_bytes(n, ck, 128);
+        }
+    }
+    return total;
+}
+
 // Workspace carve-up shared by the three convs.
 struct Workspace {
     float *slab;      // fp32 grouped slab  [ck][n_slab]
@@ -136,9 +155,21 @@ static int pick_split_k(int M, int N, long long K, int batch, int tile_m, int ti
 }
 
 // out(c_out) = W . G with the activation operand already in ws.tilesA (rows = (z,j) columns, K = ck)
-static int gemm_fwd_tiles(int c_out, int ck, int bc, long long cols, ColsView out, const Workspace &ws, cudaStream_t s) {
+static int gemm_fwd_tiles(const void *tilesA, int c_out, int ck, int bc, long long cols, ColsView out,
+                          const Workspace &ws, cudaStream_t s) {
     GemmEpilogue ep{out.ptr, cols, out.stride_z, 1, out.stride_k, false};
-    return launch_umma_gemm(ws.tilesA, ws.tilesW, (int)(bc * cols), c_out, ck, umma_trb_for(c_out), ep, 1, s);
+    return launch_umma_gemm(tilesA, ws.tilesW, (int)(bc * cols), c_out, ck, umma_trb_for(c_out), ep, 1, s);
+}
+
+// dW(c_out x ck) += dout . G with G = the forward operand tiles of this slab (rows = (z,j) columns, K = ck)
+static int gemm_dw_grouped(const void *grouped, ColsView dout, int c_out, int ck, int bc, long long cols, float *dW,
+                           const Workspace &ws, cudaStream_t s) {
+    const long long n = bc * cols;
+    const int trb = umma_trb_for(c_out);
+    SplitSrc sb{dout.ptr, HUGE_Z, 0, dout.stride_k, cols, dout.stride_z, 1};
+    int rc = launch_split_tiles(sb, ws.tilesB, c_out, n, trb, s);
+    if (rc) return rc;
+    return launch_umma_dw(grouped, ws.tilesB, ck, c_out, n, trb, dW, s);
 }
 
 // dW(c_out x ck) += dout . G^T with G^T already in ws.tilesA (rows = ck, K = (z,j) columns)
@@ -169,7 +200,7 @@ static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long
     SplitSrc src{in.ptr, cols, in.stride_z, 1, HUGE_Z, 0, in.stride_k};
     int rc = launch_split_tiles(src, ws.tilesA, n, ck, 128, s);
     if (rc) return rc;
-    return gemm_fwd_tiles(c_out, ck, bc, cols, out, ws, s);
+    return gemm_fwd_tiles(ws.tilesA, c_out, ck, bc, cols, out, ws, s);
 }
 
 // din(ck) = W^T . dout(c_out)
@@ -224,6 +255,14 @@ using namespace epn;
         EPN_REQUIRE_PTR(workspace);                                                                             \
         EPN_REQUIRE(workspace_bytes >= (need), EPN_ERR_WORKSPACE, "workspace smaller than *_workspace_bytes()"); \
         EPN_REQUIRE(((uintptr_t)workspace & 255) == 0, EPN_ERR_ALIGN, "workspace must be 256-byte aligned");      \
+    } while (0)
+
+#define EPN_CHECK_GROUPED(need)                                                                               \
+    do {                                                                                                      \
+        const size_t need__ = (need);                                                                         \
+        EPN_REQUIRE(need__ != 0, EPN_ERR_SHAPE, "grouped tiles are not available for this shape / backend");  \
+        EPN_REQUIRE(grouped_bytes == need__, EPN_ERR_WORKSPACE, "grouped_bytes != *_grouped_bytes()");        \
+        EPN_REQUIRE(((uintptr_t)grouped & 255) == 0, EPN_ERR_ALIGN, "grouped must be 256-byte aligned");      \
     } while (0)
 
 EPN_API void epn_set_slab_bytes(size_t bytes) { g_slab_bytes.store(bytes < ((size_t)64 << 10) ? ((size_t)64 << 10) : bytes); }
@@ -299,11 +338,16 @@ EPN_API size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int
     return carve(nullptr, c_in * ks, c_out, (long long)sp.bc * sp.pc * na, true).total;
 }
 
+EPN_API size_t epn_inter_so3conv_grouped_bytes(int b, int c_in, int p, int nn, int na, int ks) {
+    if (b <= 0 || c_in <= 0 || p <= 0 || nn <= 0 || na <= 0 || ks <= 0 || !inter_group_tiles_ok(nn, na, ks)) return 0;
+    return grouped_tiles_bytes(b, c_in * ks, p, na);
+}
+
 EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
                                       const int32_t *idx, const float *anchors, const float *kernels,
                                       float sigma, const float *W, float *out, void *workspace,
-                                      size_t workspace_bytes, int b, int c_in, int c_out, int p_in, int p,
-                                      int nn, int na, int ks, void *stream) {
+                                      size_t workspace_bytes, void *grouped, size_t grouped_bytes, int b, int c_in,
+                                      int c_out, int p_in, int p, int nn, int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx); EPN_REQUIRE_PTR(anchors);
     EPN_REQUIRE_PTR(kernels); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
@@ -315,6 +359,8 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     const SlabPlan sp = plan_slabs(b, ck, p, na);
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
+    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
+    uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
@@ -325,14 +371,17 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             InterGeom g{xyz + (size_t)b0 * 3 * p_in, centers + (size_t)b0 * 3 * p, anchors, kernels, sigma};
             const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;
             ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
+            void *tiles = keep ? keep : ws.tilesA;  // kept tiles: every slab has its own region
+            if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;  // 0: the grouping kernel wrote the operand tiles itself
             if (gemm_backend() == 0) {
-                direct = launch_inter_group_tiles(feats_b, idx + (size_t)b0 * p * nn, g, ws.tilesA, cdiv(ck, 32), 0, cols, 0,
+                direct = launch_inter_group_tiles(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cdiv(ck, 32), 0, cols, 0,
                                                   p0, pc, bc, c_in, p_in, p, nn, na, ks, s);
                 if (direct != 0 && direct != 1) return direct;
             }
+            EPN_REQUIRE(direct == 0 || grouped == nullptr, EPN_ERR_SHAPE, "grouped tiles requested for an unsupported shape");
             if (direct == 0) {
-                EPN_TRY(gemm_fwd_tiles(c_out, ck, bc, cols, o, ws, s));
+                EPN_TRY(gemm_fwd_tiles(tiles, c_out, ck, bc, cols, o, ws, s));
             } else {
                 EPN_TRY(launch_inter_group_fwd(feats_b, idx + (size_t)b0 * p * nn, nullptr, g, ws.slab, cols, n_slab, p0, pc,
                                                bc, c_in, p_in, p, nn, na, ks, s));
@@ -347,8 +396,9 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
 EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, const float *xyz,
                                       const float *centers, const int32_t *idx, const float *anchors,
                                       const float *kernels, float sigma, const float *W, float *dfeats,
-                                      float *dW, void *workspace, size_t workspace_bytes, int b, int c_in,
-                                      int c_out, int p_in, int p, int nn, int na, int ks, void *stream) {
+                                      float *dW, void *workspace, size_t workspace_bytes, const void *grouped,
+                                      size_t grouped_bytes, int b, int c_in, int c_out, int p_in, int p, int nn,
+                                      int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx);
     EPN_REQUIRE_PTR(anchors); EPN_REQUIRE_PTR(kernels);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
@@ -361,6 +411,8 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     const SlabPlan sp = plan_slabs(b, ck, p, na);
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
+    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
+    const uint8_t *keep = static_cast<const uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     if (dfeats != nullptr) {
         cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)b * c_in * p_in * na, s);
@@ -387,8 +439,13 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
                                                 dfeats + (size_t)b0 * c_in * p_in * na, bc, c_in, p_in, p, nn, na, ks, s);
                 if (sc != 0) return sc;
             }
-            if (dW != nullptr) {
-                // dW += dout . G^T with G recomputed (never saved by the forward)
+            const uint8_t *kept = keep;
+            if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
+            if (dW != nullptr && kept != nullptr) {
+                // dW += dout . G with G = the operand tiles the forward kept
+                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s));
+            } else if (dW != nullptr) {
+                // dW += dout . G^T with G recomputed
                 const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;
                 int direct = 1;
                 if (gemm_backend() == 0 && n_slab % 32 == 0) {
@@ -418,9 +475,14 @@ EPN_API size_t epn_intra_so3conv_workspace_bytes(int b, int c_in, int c_out, int
     return carve(nullptr, c_in * kn, c_out, (long long)sp.bc * sp.pc * na, true).total;
 }
 
+EPN_API size_t epn_intra_so3conv_grouped_bytes(int b, int c_in, int p, int na, int kn) {
+    if (b <= 0 || c_in <= 0 || p <= 0 || na <= 0 || kn <= 0 || !intra_group_tiles_ok(na, kn)) return 0;
+    return grouped_tiles_bytes(b, c_in * kn, p, na);
+}
+
 EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
-                                      void *workspace, size_t workspace_bytes, int b, int c_in, int c_out,
-                                      int p, int na, int kn, void *stream) {
+                                      void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                                      int b, int c_in, int c_out, int p, int na, int kn, void *stream) {
     EPN_REQUIRE_PTR(feats); EPN_REQUIRE_PTR(intra_idx); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
@@ -428,6 +490,8 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
     const SlabPlan sp = plan_slabs(b, ck, p, na);
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
+    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn));
+    uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
@@ -436,14 +500,17 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
             const long long cols = (long long)pc * na, n_slab = bc * cols;
             ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
+            void *tiles = keep ? keep : ws.tilesA;
+            if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;
             if (gemm_backend() == 0) {
-                direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.tilesA, 0, p0, pc, bc, c_in,
+                direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, tiles, 0, p0, pc, bc, c_in,
                                                   p, na, kn, s);
                 if (direct != 0 && direct != 1) return direct;
             }
+            EPN_REQUIRE(direct == 0 || grouped == nullptr, EPN_ERR_SHAPE, "grouped tiles requested for an unsupported shape");
             if (direct == 0) {
-                EPN_TRY(gemm_fwd_tiles(c_out, ck, bc, cols, o, ws, s));
+                EPN_TRY(gemm_fwd_tiles(tiles, c_out, ck, bc, cols, o, ws, s));
             } else {
                 EPN_TRY(launch_intra_group_fwd(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.slab, cols, n_slab, p0, pc,
                                                bc, c_in, p, na, kn, s));
@@ -457,17 +524,19 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
 
 EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
                                       const float *W, float *dfeats, float *dW, void *workspace,
-                                      size_t workspace_bytes, int b, int c_in, int c_out, int p, int na, int kn,
-                                      void *stream) {
+                                      size_t workspace_bytes, const void *grouped, size_t grouped_bytes, int b,
+                                      int c_in, int c_out, int p, int na, int kn, void *stream) {
     EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(intra_idx);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
     if (dfeats != nullptr) EPN_REQUIRE_PTR(W);
-    if (dW != nullptr) EPN_REQUIRE_PTR(feats);
+    if (dW != nullptr && grouped == nullptr) EPN_REQUIRE_PTR(feats);
     const int ck = c_in * kn;
     const SlabPlan sp = plan_slabs(b, ck, p, na);
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
+    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn));
+    const uint8_t *keep = static_cast<const uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     if (dfeats != nullptr) EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));
     if (dW != nullptr) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)c_out * ck, s);
@@ -484,7 +553,11 @@ EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, con
                 EPN_TRY(launch_intra_group_bwd(ws.slab, cols, n_slab, p0, pc, intra_idx,
                                                dfeats + (size_t)b0 * c_in * p * na, bc, c_in, p, na, kn, s));
             }
-            if (dW != nullptr) {
+            const uint8_t *kept = keep;
+            if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
+            if (dW != nullptr && kept != nullptr) {
+                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s));
+            } else if (dW != nullptr) {
                 int direct = 1;
                 if (gemm_backend() == 0) {
                     direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, ws.tilesA, 1, p0, pc, bc,

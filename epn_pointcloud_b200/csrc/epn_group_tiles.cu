@@ -237,11 +237,13 @@ static int launch_variant(const float *feats, const int32_t *idx, const InterGeo
     return check_launch("inter_group_tiles_kernel");
 }
 
+bool inter_group_tiles_ok(int nn, int na, int ks) { return ks == GT_KS && nn <= 32 && na == 60; }
+
 // Returns 1 when the shape is not covered by the tile kernel (the caller uses the slab + split path).
 int launch_inter_group_tiles(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
                              int row_limit, long long cols_per_z, int mode, int p_off, int p_cnt, int bc, int c,
                              int p_in, int p, int nn, int na, int ks, cudaStream_t s) {
-    if (ks != GT_KS || nn > 32 || na != 60 || bc > 65535) return 1;
+    if (!inter_group_tiles_ok(nn, na, ks) || bc > 65535) return 1;
     TileOut o{static_cast<uint8_t *>(tiles), k_blocks, row_limit, cols_per_z, mode};
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_GROUP);

@@ -98,11 +98,13 @@ intra_tiles_cols_kernel(const float *__restrict__ feats, const int32_t *__restri
     }
 }
 
+bool intra_group_tiles_ok(int na, int kn) { return na == 60 && kn == 12; }
+
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
                              int bc, int c, int p, int na, int kn, cudaStream_t s) {
     const long long n_slab = (long long)bc * p_cnt * na;
     const int ck = c * kn;
-    if (n_slab >= (1LL << 31) - 4096 || na != 60 || kn != 12) return 1;
+    if (n_slab >= (1LL << 31) - 4096 || !intra_group_tiles_ok(na, kn)) return 1;
     const long long rows = mode == 0 ? n_slab : ck, K = mode == 0 ? ck : n_slab;
     const int rows_pad = (int)((rows + 127) / 128 * 128), k_blocks = (int)((K + KB - 1) / KB);
     const int kcgs = k_blocks * (KB / 8);

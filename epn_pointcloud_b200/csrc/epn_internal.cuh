@@ -93,6 +93,16 @@ int umma_trb_for(int n_rows);
 int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
                      const GemmEpilogue &ep, int split_k, cudaStream_t s);
 
+// epn_gemm_dw.cu -- dW[c_out, ck] += dout . G straight from the forward operand tiles of a slab
+// (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles
+// (rows = c_out in trb-row tiles, K = n).
+int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, long long n, int trb, float *dW,
+                   cudaStream_t s);
+
+// shapes the direct-to-tiles grouping kernels cover
+bool inter_group_tiles_ok(int nn, int na, int ks);
+bool intra_group_tiles_ok(int na, int kn);
+
 // epn_gemm_simt.cu
 int launch_sgemm(const GemmOperand &A, const GemmOperand &B, float *C, long long c_stride_z, long long ldc,
                  int M, int N, int K, int batch, int split_k, int accumulate, cudaStream_t s);

@@ -106,7 +106,9 @@ class _BasicConvFn(torch.autograd.Function):
 
 
 class _InterSO3ConvFn(torch.autograd.Function):
-    """Saves only feats, W and the index/geometry tensors; G and inter_w are recomputed in backward."""
+    """Saves feats, W, the index/geometry tensors and -- memory permitting (ops.set_keep_grouped) -- the bf16
+    operand tiles of the grouped tensor, from which backward takes dW; inter_w never exists, and without the
+    kept tiles G is recomputed."""
 
     @staticmethod
     def forward(ctx, feats, W, xyz, centers, idx, anchors, kernels, sigma):
@@ -115,7 +117,9 @@ class _InterSO3ConvFn(torch.autograd.Function):
         ctx.sigma = sigma
         ctx.has_feats = feats is not None
         ctx.save_for_backward(*( [feats] if feats is not None else [] ), W, xyz, centers, idx, anchors, kernels)
-        return ops.inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W)
+        out, ctx.grouped = ops.inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W,
+                                                 keep_grouped=ctx.needs_input_grad[1])
+        return out
 
     @staticmethod
     def backward(ctx, dout):
@@ -124,7 +128,8 @@ class _InterSO3ConvFn(torch.autograd.Function):
         W, xyz, centers, idx, anchors, kernels = saved
         need_df = ctx.has_feats and ctx.needs_input_grad[0]
         dfeats, dW = ops.inter_so3conv_bwd(dout.contiguous(), feats, xyz, centers, idx, anchors, kernels, ctx.sigma, W,
-                                           need_dfeats=need_df, need_dw=ctx.needs_input_grad[1])
+                                           need_dfeats=need_df, need_dw=ctx.needs_input_grad[1], grouped=ctx.grouped)
+        ctx.grouped = None
         return dfeats, dW, None, None, None, None, None, None
 
 
@@ -134,13 +139,15 @@ class _IntraSO3ConvFn(torch.autograd.Function):
         feats = feats.contiguous()
         W = W.contiguous()
         ctx.save_for_backward(feats, W, intra_idx)
-        return ops.intra_so3conv_fwd(feats, intra_idx, W)
+        out, ctx.grouped = ops.intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=ctx.needs_input_grad[1])
+        return out
 
     @staticmethod
     def backward(ctx, dout):
         feats, W, intra_idx = ctx.saved_tensors
         dfeats, dW = ops.intra_so3conv_bwd(dout.contiguous(), feats, intra_idx, W, ctx.needs_input_grad[0],
-                                           ctx.needs_input_grad[1])
+                                           ctx.needs_input_grad[1], grouped=ctx.grouped)
+        ctx.grouped = None
         return dfeats, dW, None
 
 

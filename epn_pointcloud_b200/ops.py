@@ -275,8 +275,50 @@ def basic_conv_bwd(dout, x, W, need_dx=True, need_dw=True):
     return dx, dW
 
 
-def inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W):
-    """Fused InterSO3Conv minus sampling/ball query -> [b,c_out,p,na].  feats None = occupancy ones."""
+def _grouped_buffer(nbytes, device, keep_grouped):
+    """uint8 buffer for the operand tiles a training forward keeps, or None (see set_keep_grouped)."""
+    if not keep_grouped or nbytes == 0:
+        return None
+    mode = keep_grouped_mode()
+    if mode == "off":
+        return None
+    if mode == "auto":
+        free, _ = torch.cuda.mem_get_info(device)
+        free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+        if nbytes > _KEEP_FRACTION * free:
+            return None
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
+_KEEP_FRACTION = 0.25
+_keep_mode = None
+
+
+def keep_grouped_mode():
+    """'auto' (default): a forward under autograd keeps the grouped operand tiles for dW when they take less
+    than a quarter of the free device memory; 'on': always; 'off': never (dW recomputes the grouping).
+    Initial value from EPN_KEEP_GROUPED."""
+    global _keep_mode
+    if _keep_mode is None:
+        import os
+        v = os.environ.get("EPN_KEEP_GROUPED", "auto").lower()
+        _keep_mode = {"1": "on", "0": "off"}.get(v, v)
+        if _keep_mode not in ("auto", "on", "off"):
+            raise RuntimeError("EPN_KEEP_GROUPED must be auto, on or off")
+    return _keep_mode
+
+
+def set_keep_grouped(mode):
+    global _keep_mode
+    if mode not in ("auto", "on", "off"):
+        raise ValueError("mode must be 'auto', 'on' or 'off'")
+    _keep_mode = mode
+
+
+def inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W, keep_grouped=False):
+    """Fused InterSO3Conv minus sampling/ball query -> [b,c_out,p,na].  feats None = occupancy ones.
+    keep_grouped=True returns (out, grouped) with grouped = the kept operand tiles (or None) for
+    inter_so3conv_bwd(..., grouped=grouped)."""
     _require_cuda(feats, xyz, centers, idx, anchors, kernels, W)
     b, _, p_in = xyz.shape
     p, nn = idx.shape[1], idx.shape[2]
@@ -290,13 +332,17 @@ def inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W):
     with torch.cuda.device(xyz.device):
         wsb = L.epn_inter_so3conv_workspace_bytes(b, c_in, c_out, p_in, p, nn, na, ks, 0)
         ws = _workspace(wsb, xyz.device)
+        grouped = _grouped_buffer(L.epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks) if keep_grouped else 0,
+                                  xyz.device, keep_grouped)
         _lib.check(L.epn_inter_so3conv_fwd_f32(_p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors), _p(kernels),
-                                               float(sigma), _p(W), _p(out), _p(ws), wsb, b, c_in, c_out, p_in, p, nn,
+                                               float(sigma), _p(W), _p(out), _p(ws), wsb, _p(grouped),
+                                               0 if grouped is None else grouped.numel(), b, c_in, c_out, p_in, p, nn,
                                                na, ks, _stream()), "epn_inter_so3conv_fwd_f32")
-    return out
+    return (out, grouped) if keep_grouped else out
 
 
-def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W, need_dfeats=True, need_dw=True):
+def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W, need_dfeats=True, need_dw=True,
+                      grouped=None):
     _require_cuda(dout, feats, xyz, centers, idx, anchors, kernels, W)
     b, _, p_in = xyz.shape
     p, nn = idx.shape[1], idx.shape[2]
@@ -311,14 +357,16 @@ def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W
         wsb = L.epn_inter_so3conv_workspace_bytes(b, c_in, c_out, p_in, p, nn, na, ks, 1)
         ws = _workspace(wsb, dout.device)
         _lib.check(L.epn_inter_so3conv_bwd_f32(_p(dout), _p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors),
-                                               _p(kernels), float(sigma), _p(W), _p(dfeats), _p(dW), _p(ws), wsb, b,
+                                               _p(kernels), float(sigma), _p(W), _p(dfeats), _p(dW), _p(ws), wsb,
+                                               _p(grouped), 0 if grouped is None else grouped.numel(), b,
                                                c_in, c_out, p_in, p, nn, na, ks, _stream()),
                    "epn_inter_so3conv_bwd_f32")
     return dfeats, dW
 
 
-def intra_so3conv_fwd(feats, intra_idx, W):
-    """Fused IntraSO3Conv: feats [b,c,p,na], intra_idx int32 [na,kn], W [co, c*kn] -> [b,co,p,na]."""
+def intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=False):
+    """Fused IntraSO3Conv: feats [b,c,p,na], intra_idx int32 [na,kn], W [co, c*kn] -> [b,co,p,na]
+    (keep_grouped: as inter_so3conv_fwd)."""
     _require_cuda(feats, intra_idx, W)
     b, c_in, p, na = feats.shape
     kn = intra_idx.shape[1]
@@ -330,12 +378,15 @@ def intra_so3conv_fwd(feats, intra_idx, W):
     with torch.cuda.device(feats.device):
         wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 0)
         ws = _workspace(wsb, feats.device)
-        _lib.check(L.epn_intra_so3conv_fwd_f32(_p(feats), _p(intra_idx), _p(W), _p(out), _p(ws), wsb, b, c_in, c_out,
+        grouped = _grouped_buffer(L.epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn) if keep_grouped else 0,
+                                  feats.device, keep_grouped)
+        _lib.check(L.epn_intra_so3conv_fwd_f32(_p(feats), _p(intra_idx), _p(W), _p(out), _p(ws), wsb, _p(grouped),
+                                               0 if grouped is None else grouped.numel(), b, c_in, c_out,
                                                p, na, kn, _stream()), "epn_intra_so3conv_fwd_f32")
-    return out
+    return (out, grouped) if keep_grouped else out
 
 
-def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True):
+def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True, grouped=None):
     _require_cuda(dout, feats, intra_idx, W)
     b, c_in, p, na = feats.shape
     kn = intra_idx.shape[1]
@@ -347,7 +398,8 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True)
         wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 1)
         ws = _workspace(wsb, feats.device)
         _lib.check(L.epn_intra_so3conv_bwd_f32(_p(dout), _p(feats), _p(intra_idx), _p(W), _p(dfeats), _p(dW), _p(ws),
-                                               wsb, b, c_in, c_out, p, na, kn, _stream()),
+                                               wsb, _p(grouped), 0 if grouped is None else grouped.numel(), b, c_in,
+                                               c_out, p, na, kn, _stream()),
                    "epn_intra_so3conv_bwd_f32")
     return dfeats, dW
 

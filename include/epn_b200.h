@@ -137,33 +137,45 @@ int epn_intra_group_bwd_f32(const float *dout, const int32_t *intra_idx, float *
  *   out[b,o,p,a] = sum_{c,k} W[o,c*ks+k] * sum_n w(b,p,a,k,n) * feats[b,c,idx[b,p,n],a]
  * feats == NULL means feats == 1 with c_in == 1 (layer 0: occupancy features,
  * so3conv/functional.py:25-44).  inter_w is never materialised.
- * workspace: epn_inter_so3conv_workspace_bytes(...) bytes, 256-B aligned. */
+ * workspace: epn_inter_so3conv_workspace_bytes(...) bytes, 256-B aligned.
+ *
+ * grouped (optional, NULL = off): what autograd would keep of the grouped tensor for the weight gradient
+ * (the reference keeps the whole [b,c,ks,p,na] fp32 tensor, so3conv/modules.py:48-55 under autograd).
+ * A training forward may pass a buffer of exactly epn_*_grouped_bytes(...) bytes (256-B aligned); the
+ * tensor-core operand tiles of the grouped tensor are then written there instead of into the workspace, and
+ * a backward given the same buffer computes dW from them without re-running the spatial contraction.
+ * epn_*_grouped_bytes returns 0 when the shape / backend cannot do that (then pass NULL).  The slab size
+ * (epn_set_slab_bytes) and GEMM backend must not change between that forward and its backward. */
 size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int p_in, int p, int nn, int na,
                                          int ks, int backward);
+size_t epn_inter_so3conv_grouped_bytes(int b, int c_in, int p, int nn, int na, int ks);
 int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
                               const int32_t *idx, const float *anchors, const float *kernels,
                               float sigma, const float *W, float *out, void *workspace,
-                              size_t workspace_bytes, int b, int c_in, int c_out, int p_in, int p,
-                              int nn, int na, int ks, void *stream);
+                              size_t workspace_bytes, void *grouped, size_t grouped_bytes, int b, int c_in,
+                              int c_out, int p_in, int p, int nn, int na, int ks, void *stream);
 /* dout [b,c_out,p,na] -> dfeats [b,c_in,p_in,na] (NULL to skip; else fully
  * written) and dW [c_out,c_in*ks] (NULL to skip; else fully written). */
 int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, const float *xyz,
                               const float *centers, const int32_t *idx, const float *anchors,
                               const float *kernels, float sigma, const float *W, float *dfeats,
-                              float *dW, void *workspace, size_t workspace_bytes, int b, int c_in,
-                              int c_out, int p_in, int p, int nn, int na, int ks, void *stream);
+                              float *dW, void *workspace, size_t workspace_bytes, const void *grouped,
+                              size_t grouped_bytes, int b, int c_in, int c_out, int p_in, int p, int nn,
+                              int na, int ks, void *stream);
 
 /* IntraSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:197-200):
  *   out[b,o,p,a] = sum_{c,k} W[o,c*kn+k] * feats[b,c,p,intra_idx[a,k]] */
 size_t epn_intra_so3conv_workspace_bytes(int b, int c_in, int c_out, int p, int na, int kn,
                                          int backward);
+size_t epn_intra_so3conv_grouped_bytes(int b, int c_in, int p, int na, int kn);
 int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
-                              void *workspace, size_t workspace_bytes, int b, int c_in, int c_out,
-                              int p, int na, int kn, void *stream);
+                              void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                              int b, int c_in, int c_out, int p, int na, int kn, void *stream);
+/* feats may be NULL when grouped is given (dW then needs nothing else). */
 int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
                               const float *W, float *dfeats, float *dW, void *workspace,
-                              size_t workspace_bytes, int b, int c_in, int c_out, int p, int na,
-                              int kn, void *stream);
+                              size_t workspace_bytes, const void *grouped, size_t grouped_bytes, int b,
+                              int c_in, int c_out, int p, int na, int kn, void *stream);
 
 /* BasicSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:48-55) on an already
  * grouped tensor: x [b, ck, pa], W [co, ck] -> out [b, co, pa].

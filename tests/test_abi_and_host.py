@@ -45,8 +45,14 @@ def test_version_and_argument_errors_without_gpu():
     p = ctypes.cast(buf, ctypes.c_void_p)
     rc = L.epn_ball_query_f32(p, p, p, 0, 8, 8, 0.1, 4, None)
     assert rc == -2 and b"must be > 0" in L.epn_last_error()
-    rc = L.epn_inter_so3conv_fwd_f32(None, p, p, p, p, p, 0.1, p, p, p, 16, 1, 4, 4, 8, 8, 4, 60, 24, None)
+    rc = L.epn_inter_so3conv_fwd_f32(None, p, p, p, p, p, 0.1, p, p, p, 16, None, 0, 1, 4, 4, 8, 8, 4, 60, 24, None)
     assert rc == -1  # feats NULL with c_in != 1
+    # kept operand tiles: one 128-row tile per 128 grouped columns, 4 bytes (bf16 hi+lo) per element, and
+    # only for shapes the tile kernels cover with whole tiles
+    assert L.epn_inter_so3conv_grouped_bytes(2, 4, 64, 16, 60, 24) == 2 * 64 * 60 * 96 * 4
+    assert L.epn_inter_so3conv_grouped_bytes(2, 4, 64, 16, 20, 24) == 0  # 20 anchors: generic path
+    assert L.epn_inter_so3conv_grouped_bytes(1, 4, 10, 16, 60, 24) == 0  # 600 columns: not whole tiles
+    assert L.epn_intra_so3conv_grouped_bytes(2, 8, 64, 60, 12) == 2 * 64 * 60 * 96 * 4
     wsb = L.epn_inter_so3conv_workspace_bytes(2, 4, 8, 64, 64, 16, 60, 24, 0)
     slab = 2 * 4 * 24 * 64 * 60 * 4  # one fp32 slab + its bf16 hi/lo operand tiles + weight tiles
     assert wsb % 256 == 0 and 2 * slab <= wsb <= 4 * slab

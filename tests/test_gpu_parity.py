@@ -397,8 +397,18 @@ def test_error_behaviour_on_device(E):
     with pytest.raises(RuntimeError):
         E.ops.ball_query(x.permute(0, 2, 1), x, 0.1, 4)  # non-contiguous
     rc = L.epn_inter_so3conv_fwd_f32(None, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 0.1,
-                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, 1, 1, 4, 8, 8, 4, 60, 24, None)
+                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, None, 0, 1, 1, 4, 8, 8, 4, 60, 24, None)
     assert rc == -3 and b"workspace" in L.epn_last_error()
+    # a kept-tiles buffer of the wrong size, or for a shape without whole tiles, is refused
+    f = torch.zeros(1, 4, 64, 60, device=DEV)
+    idx = torch.arange(60, device=DEV, dtype=torch.int32).view(60, 1).repeat(1, 12).contiguous()
+    W = torch.zeros(8, 48, device=DEV)
+    out = torch.empty(1, 8, 64, 60, device=DEV)
+    wsb = L.epn_intra_so3conv_workspace_bytes(1, 4, 8, 64, 60, 12, 0)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+    rc = L.epn_intra_so3conv_fwd_f32(f.data_ptr(), idx.data_ptr(), W.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb,
+                                     ws.data_ptr(), 1024, 1, 4, 8, 64, 60, 12, None)
+    assert rc == -3 and b"grouped_bytes" in L.epn_last_error()
 
 
 # ------------------------------------------- tcgen05 GEMM engine vs the fp32 SIMT cross-check
@@ -470,6 +480,55 @@ def test_umma_engine_many_slabs(E, both_backends, monkeypatch):
     for key, val in res.items():
         for a, b_, name in zip(val, ref, ("out", "dfeats", "dW")):
             assert rel_err(a, b_) < 3e-5, (key, name)
+
+
+@pytest.mark.parametrize("kind,c_in,c_out,p,nn_,slab", [
+    ("inter", 16, 24, 64, 16, None), ("inter", 16, 24, 64, 16, 8 << 20), ("inter", 64, 128, 256, 32, None),
+    ("inter", 128, 256, 128, 16, None), ("inter0", 1, 64, 256, 32, None),
+    ("intra", 16, 40, 64, 0, None), ("intra", 16, 40, 64, 0, 4 << 20), ("intra", 256, 256, 64, 0, None),
+])
+def test_dw_from_kept_forward_tiles_equals_recomputed(E, kind, c_in, c_out, p, nn_, slab):
+    """dW read from the operand tiles the forward kept (MN-major tcgen05 operand) vs dW from a re-run grouping,
+    incl. several slabs per call, a C_out that needs two 128-column passes and the 24-row layer-0 matrix."""
+    from epn_pointcloud_b200 import _lib
+    L = _lib.lib()
+    b = 3
+    old = L.epn_get_slab_bytes()
+    torch.manual_seed(1)
+    if kind == "intra":
+        conv = E.IntraSO3Conv(c_in, c_out).to(DEV)
+    else:
+        conv = _layer(E, c_in, c_out, 1, nn_, 0.45, 0.1)
+    xyz = sphere(b, p, 23).to(DEV)
+    res = {}
+    try:
+        if slab:
+            L.epn_set_slab_bytes(slab)
+        nbytes = (L.epn_intra_so3conv_grouped_bytes(b, c_in, p, 60, 12) if kind == "intra" else
+                  L.epn_inter_so3conv_grouped_bytes(b, c_in, p, nn_, 60, 24))
+        assert nbytes == b * p * 60 * ((c_in * (12 if kind == "intra" else 24) + 31) // 32 * 32) * 4
+        for mode in ("off", "on"):
+            E.ops.set_keep_grouped(mode)
+            f = None
+            if kind != "inter0":
+                f = torch.randn(b, c_in, p, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(9)).requires_grad_(True)
+            conv.zero_grad()
+            if kind == "intra":
+                y = conv(E.SphericalPointCloud(None, f, None)).feats
+                kept = E.ops.intra_so3conv_fwd(f.detach(), conv._intra_idx32, conv.basic_conv.W.detach(), keep_grouped=True)[1]
+                assert (kept is not None and kept.numel() == nbytes) if mode == "on" else kept is None
+            else:
+                y = conv(E.SphericalPointCloud(xyz, f, None))[3].feats
+            r = torch.randn(y.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(10))
+            (y * r).sum().backward()
+            res[mode] = (y.detach(), conv.basic_conv.W.grad.detach().clone(), None if f is None else f.grad.detach())
+    finally:
+        L.epn_set_slab_bytes(old)
+        E.ops.set_keep_grouped("auto")
+    assert torch.equal(res["on"][0], res["off"][0])          # same tiles, same GEMM: bit-identical forward
+    assert rel_err(res["on"][1], res["off"][1]) < 5e-6       # same products, different summation order
+    if res["on"][2] is not None:
+        assert torch.equal(res["on"][2], res["off"][2]) or rel_err(res["on"][2], res["off"][2]) < 1e-6
 
 
 # ------------------------------ shapes of the other BASELINE configs (rotation model, 3DMatch model, sweep)
