@@ -33,12 +33,26 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    """nvcc -> epn_pointcloud_b200/libepn_b200.so (cross-compiles without a GPU)."""
+    """nvcc -> epn_pointcloud_b200/libepn_b200.so (cross-compiles without a GPU).  Every .cu is compiled to
+    an object under csrc/build/ (in parallel, re-used while newer than the source and every header), then linked."""
     if not force and not _stale():
         return _SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", _SO] + sources()
-    subprocess.check_call(cmd)
+    objdir = os.path.join(_CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    headers = glob.glob(os.path.join(_CSRC, "*.cuh")) + [_HEADER]
+    hdr_t = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t):
+            jobs.append((src, subprocess.Popen([nvcc] + flags + ["-c", "-o", obj, src])))
+    failed = [src for src, j in jobs if j.wait() != 0]
+    if failed:
+        raise RuntimeError("nvcc failed for %s" % ", ".join(failed))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", _SO] + objs)
     return _SO
 
 

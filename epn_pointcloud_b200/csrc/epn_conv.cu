@@ -214,7 +214,8 @@ static int gemm_dx(const float *W, int c_out, int ck, ColsView dout, int bc, lon
     // orientation: D[rows = (c,k), cols = (z,j)] so that an epilogue thread owns one (c,k) row and writes
     // runs of consecutive columns as 16-byte vectors (din is column-contiguous)
     const long long n = bc * cols;
-    const int trn = umma_trb_for((int)(n < 256 ? n : 256));
+    static const int trn_max = getenv("EPN_DX_TRN") ? atoi(getenv("EPN_DX_TRN")) : 256;
+    const int trn = umma_trb_for((int)(n < trn_max ? n : trn_max));
     SplitSrc src{dout.ptr, cols, dout.stride_z, 1, HUGE_Z, 0, dout.stride_k};
     int rc = launch_split_tiles(src, ws.tilesA, n, c_out, trn, s);
     if (rc) return rc;

@@ -8,6 +8,8 @@
 //
 // Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 bulk-copy
 // producer (one elected lane), warp 5 TMEM allocator + MMA issuer (one elected lane).
+#include <stdlib.h>
+
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
@@ -231,31 +233,36 @@ umma_gemm_kernel(UmmaGemmParams p) {
                 for (int cc = 0; cc < gw; cc += 32) {
                     float v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g0 + cc), v);
+                    if (cc == 0 && g0 > 0) {  // the previous group's rows have left the staging buffer
+                        bulk_wait_read0();
+                        __syncwarp();
+                    }
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         if (cc + j < gw)
                             *reinterpret_cast<float4 *>(stg + (size_t)lane * (gw + 4) + cc + j) =
                                 make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
+                fence_proxy_async_smem();  // this lane's staging writes -> visible to the bulk-copy engine
                 __syncwarp();
-                const long long col = (long long)blockIdx.y * p.trb + g0 + 4 * lane;
-                if (4 * lane < gw && g0 + 4 * lane < p.trb && col < p.n_valid) {
-                    const long long coff = col_offset((uint32_t)col, 1);
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const long long r = row0 + rr;
-                        if (r >= p.m_valid) break;
-                        float *dst = p.out + row_offset(r) + coff;
-                        const float4 val = *reinterpret_cast<const float4 *>(stg + (size_t)rr * (gw + 4) + 4 * lane);
-                        if (col + 3 < p.n_valid) {
-                            *reinterpret_cast<float4 *>(dst) = val;
-                        } else {
-                            const float t[4] = {val.x, val.y, val.z, val.w};
-                            for (int e = 0; e < 4 && col + e < p.n_valid; ++e) dst[e] = t[e];
-                        }
+                // one asynchronous bulk store per staged row (<= 512 contiguous bytes): the warp goes straight
+                // back to TMEM while the copy engine streams the rows out
+                const long long colg = (long long)blockIdx.y * p.trb + g0;
+                const long long r = row0 + lane;
+                if (r < p.m_valid && colg < p.n_valid) {
+                    const int ncols = (int)min((long long)min(gw, p.trb - g0), (long long)p.n_valid - colg);
+                    float *dst = p.out + row_offset(r) + col_offset((uint32_t)colg, 1);
+                    const float *src = stg + (size_t)lane * (gw + 4);
+                    const bool whole = !col_split || ((uint32_t)colg / cpz == (uint32_t)(colg + ncols - 1) / cpz);
+                    if (whole && (ncols & 3) == 0) {
+                        bulk_s2g(dst, smem_u32(src), (uint32_t)ncols * 4u);
+                    } else {
+                        for (int e = 0; e < ncols; ++e) p.out[row_offset(r) + col_offset((uint32_t)(colg + e), 1)] = src[e];
                     }
                 }
-                __syncwarp();
+                bulk_commit();
             }
+            bulk_wait_read0();  // shared memory must stay valid until the copy engine has read it
         } else
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
@@ -321,6 +328,8 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     int stages = (int)((200 * 1024) / stage);
     if (stages > 4) stages = 4;
     if (trb <= 128 && stages > 3) stages = 3;  // 2 CTAs per SM
+    static const int st_small = getenv("EPN_DX_STAGES") ? atoi(getenv("EPN_DX_STAGES")) : 0;
+    if (st_small && trb <= 128 && K <= 256) stages = st_small;
     if (trb > 128) stages = 2;                 // 96 KB per CTA: 2 CTAs per SM (2 x 256 TMEM columns), the
                                                // epilogue of one overlaps the main loop of the other
     if (stages < 2) stages = 2;

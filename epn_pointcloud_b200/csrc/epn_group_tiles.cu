@@ -102,8 +102,9 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
         Fs[(bc * NN + n) * NA + e] = 0.f;
     }
 
-    // kernel weights of this thread's (anchor, kernel-point group): registers for the whole point
-    float w[KG][NN];
+    // kernel weights of this thread's (anchor, kernel-point group): registers for the whole point, packed as
+    // (even neighbour, odd neighbour) pairs for the fp32x2 FMAs of the contraction
+    uint64_t w2[KG][NN / 2];
     {
         float R[9];
 #pragma unroll
@@ -115,9 +116,15 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
             const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
                         rz = R[6] * kx + R[7] * ky + R[8] * kz;
 #pragma unroll
-            for (int n = 0; n < NN; ++n) {
-                const float v = kernel_weight_fast(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, 1.0f / g.sigma);
-                w[i][n] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
+            for (int n = 0; n < NN; n += 2) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float t = kernel_weight_fast(s_g[(n + e) * 3], s_g[(n + e) * 3 + 1], s_g[(n + e) * 3 + 2], rx, ry, rz,
+                                                       1.0f / g.sigma);
+                    v[e] = (a_ok && n + e < nn) ? t * s_mult[n + e] : 0.f;
+                }
+                w2[i][n / 2] = pack_f32x2(v[0], v[1]);
             }
         }
     }
@@ -159,22 +166,31 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
         float *gbase = Gs + (size_t)k0 * GSTR + aa;
 #pragma unroll 2
         for (int cl = 0; cl < CCH; ++cl) {
-            float acc[KG];
+            // acc2[i] = (sum over even neighbours, sum over odd neighbours) of w * f
+            uint64_t acc2[KG];
 #pragma unroll
-            for (int i = 0; i < KG; ++i) acc[i] = 0.f;
+            for (int i = 0; i < KG; ++i) acc2[i] = 0ull;
             if (chunk * CCH + cl < c) {
                 const float *frow = fbase + cl * NN * NA;
 #pragma unroll
                 for (int n4 = 0; n4 < NN; n4 += 4) {
                     if (n4 < nn) {  // CTA-uniform: whole groups of 4 absent neighbours are skipped
 #pragma unroll
-                        for (int n = n4; n < n4 + 4; ++n) {
-                            const float f = HAS_FEATS ? frow[n * NA] : 1.0f;  // occupancy features == 1
+                        for (int n = n4; n < n4 + 4; n += 2) {
+                            // occupancy features == 1 when there is nothing to gather
+                            const uint64_t f2 = HAS_FEATS ? pack_f32x2(frow[n * NA], frow[(n + 1) * NA]) : pack_f32x2(1.0f, 1.0f);
 #pragma unroll
-                            for (int i = 0; i < KG; ++i) acc[i] = fmaf(w[i][n], f, acc[i]);
+                            for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(w2[i][n / 2], f2, acc2[i]);
                         }
                     }
                 }
+            }
+            float acc[KG];
+#pragma unroll
+            for (int i = 0; i < KG; ++i) {
+                float e, o;
+                unpack_f32x2(acc2[i], e, o);
+                acc[i] = e + o;
             }
             if (a_ok) {
 #pragma unroll

@@ -181,7 +181,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     nn = s_nu;  // number of DISTINCT neighbours
     const bool grp_active = n0 < nn;  // warp-uniform: this thread's 4 neighbours exist
 
-    float w[SC_KS][SC_NB];
+    uint64_t w2[SC_KS][SC_NB / 2];  // (neighbour 2j, neighbour 2j+1) pairs for the fp32x2 FMAs
     {
         float R[9];
 #pragma unroll
@@ -191,12 +191,15 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
             const float kx = __ldg(g.kernels + k * 3), ky = __ldg(g.kernels + k * 3 + 1), kz = __ldg(g.kernels + k * 3 + 2);
             const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
                         rz = R[6] * kx + R[7] * ky + R[8] * kz;
+            float wv[SC_NB];
 #pragma unroll
             for (int j = 0; j < SC_NB; ++j) {
                 const int n = n0 + j;
                 const float v = kernel_weight_fast(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, 1.0f / g.sigma);
-                w[k][j] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
+                wv[j] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
             }
+#pragma unroll
+            for (int j = 0; j < SC_NB; j += 2) w2[k][j / 2] = pack_f32x2(wv[j], wv[j + 1]);
         }
     }
     // destination rows of this thread's 4 neighbours (element offset of [q, a] inside one channel plane)
@@ -237,16 +240,20 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
         for (int cl = 0; cl < SC_CCH; ++cl) {
             const int cc = chunk * SC_CCH + cl;
             if (cc >= c || !grp_active) break;  // idle neighbour groups only keep the barriers company
-            float t[SC_NB];
+            uint64_t t2[SC_NB / 2];
 #pragma unroll
-            for (int j = 0; j < SC_NB; ++j) t[j] = 0.f;
+            for (int j = 0; j < SC_NB / 2; ++j) t2[j] = 0ull;
             const float *drow = dbase + cl * SC_KS * NA;
 #pragma unroll
             for (int k = 0; k < SC_KS; ++k) {
                 const float dv = drow[k * NA];
+                const uint64_t d2 = pack_f32x2(dv, dv);
 #pragma unroll
-                for (int j = 0; j < SC_NB; ++j) t[j] = fmaf(w[k][j], dv, t[j]);
+                for (int j = 0; j < SC_NB / 2; ++j) t2[j] = fma_f32x2(w2[k][j], d2, t2[j]);
             }
+            float t[SC_NB];
+#pragma unroll
+            for (int j = 0; j < SC_NB / 2; ++j) unpack_f32x2(t2[j], t[2 * j], t[2 * j + 1]);
             float *dplane = DF + (size_t)cc * cplane;
 #pragma unroll
             for (int j = 0; j < SC_NB; ++j)

@@ -32,6 +32,23 @@ __device__ __forceinline__ float kernel_weight_fast(float gx, float gy, float gz
     return fmaxf(fmaf(-d, inv_sigma, 1.0f), 0.0f);
 }
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 retires two fp32 FMAs per issue slot at the same peak FLOP/s as
+// two FFMAs -- measured 73.8 vs 72.5 TFLOP/s -- so issue-bound FMA loops need half the instructions).
+// Each half is an ordinary IEEE fp32 fma.rn.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // Matrix operand of the generic GEMM: element (row, col) of slice z lives at
 // ptr + z*stride_z + row*stride_row + col*stride_col.  For A rows are m and
 // cols are k; for B rows are k and cols are n.

@@ -72,6 +72,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src_gmem
                  ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
 
+// shared -> global bulk store (bulk_group completion): the issuing thread's earlier generic-proxy writes to
+// the source must be made visible with fence_proxy_async_smem() by their writers first.
+__device__ __forceinline__ void bulk_s2g(void *dst_gmem, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all bulk groups of this thread have finished READING their shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {  // whole warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -20,6 +20,39 @@ import torch.nn.functional as F
 from oracle import epn_oracle as O
 
 
+class _RefCudaOps:
+    """Index ops for CUDA tensors: the REFERENCE's own CUDA kernels (oracle/_ref, built by oracle/build_ref.py
+    from vgtk/vgtk/cuda/*), so that running this port on a GPU is the reference's GPU path -- its PyTorch op
+    chain plus its native extensions -- and not anything of the product library."""
+    _mods = {}
+
+    @classmethod
+    def _mod(cls, ext):
+        if ext not in cls._mods:
+            from oracle import build_ref
+            m = build_ref.load_ref(ext)
+            if m is None:
+                raise RuntimeError("oracle/_ref/vgtk_ref_%s.so is missing (python -m oracle.build_ref)" % ext)
+            cls._mods[ext] = m
+        return cls._mods[ext]
+
+    @classmethod
+    def furthest_point_sampling(cls, xyz, m):
+        return cls._mod("grouping").furthest_point_sampling(xyz.contiguous(), m)
+
+    @classmethod
+    def ball_query(cls, new_xyz, xyz, radius, nsample):
+        return cls._mod("grouping").ball_query(new_xyz.contiguous(), xyz.contiguous(), radius, nsample)
+
+    @classmethod
+    def gather_points_forward(cls, points, idx):
+        return cls._mod("gathering").gather_points_forward(points.contiguous(), idx.contiguous())
+
+
+def _ops(t):
+    return _RefCudaOps if t.is_cuda else O
+
+
 # ------------------------------------------------------------------ sampling
 def sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample):
     """vgtk/vgtk/spconv/functional.py:412-421 + vgtk/vgtk/pc/sample.py:46-77.
@@ -27,12 +60,12 @@ def sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample):
     b, _, p_in = xyz.shape
     n_sample = math.ceil(p_in / stride)
     if p_in == n_sample or lazy_sample:
-        sample_idx = torch.arange(n_sample, dtype=torch.int32).view(1, -1).expand(b, -1).contiguous()
+        sample_idx = torch.arange(n_sample, dtype=torch.int32, device=xyz.device).view(1, -1).expand(b, -1).contiguous()
     else:
-        sample_idx = O.furthest_point_sampling(xyz, n_sample)
-    new_xyz = O.gather_points_forward(xyz, sample_idx)
-    ball_idx = O.ball_query(new_xyz, xyz, radius, n_neighbor)
-    grouped = O.gather_points_forward(xyz, ball_idx.view(b, -1)).view(b, 3, n_sample, n_neighbor)
+        sample_idx = _ops(xyz).furthest_point_sampling(xyz, n_sample)
+    new_xyz = _ops(xyz).gather_points_forward(xyz, sample_idx)
+    ball_idx = _ops(xyz).ball_query(new_xyz, xyz, radius, n_neighbor)
+    grouped = _ops(xyz).gather_points_forward(xyz, ball_idx.view(b, -1)).view(b, 3, n_sample, n_neighbor)
     return grouped - new_xyz.unsqueeze(3), ball_idx, sample_idx, new_xyz
 
 
@@ -80,7 +113,7 @@ def inter_so3conv(xyz, feats, W, anchors, kernels, stride, n_neighbor, radius, s
     grouped_xyz, inter_idx, sample_idx, new_xyz = sample_and_query(xyz, stride, radius, n_neighbor, lazy_sample)
     inter_w = inter_weights(grouped_xyz.to(feats.dtype), anchors.to(feats.dtype), kernels.to(feats.dtype), sigma)
     b, c, _, a = feats.shape
-    feats_sh = torch.cat((feats, torch.zeros(b, c, 1, a, dtype=feats.dtype)), dim=2).contiguous()
+    feats_sh = torch.cat((feats, torch.zeros(b, c, 1, a, dtype=feats.dtype, device=feats.device)), dim=2).contiguous()
     grouped = inter_group(inter_idx, inter_w, feats_sh)
     return inter_idx, inter_w, sample_idx, new_xyz, basic_conv(grouped, W)
 
@@ -128,7 +161,7 @@ def backbone_forward(x, layers, dtype=torch.float32):
     b, n, _ = x.shape
     xyz = x.permute(0, 2, 1).contiguous()
     na = layers[0][3].shape[0]
-    feats = torch.ones(b, 1, n, na, dtype=dtype)  # dtype=float64 gives the "true" value the fp32 paths round
+    feats = torch.ones(b, 1, n, na, dtype=dtype, device=x.device)  # dtype=float64 gives the "true" value the fp32 paths round
     for prm, args, intra_idx, anchors, kernels in layers:
         xyz, feats = separable_block(xyz, feats, prm, args, intra_idx, anchors, kernels)
     return xyz, feats
