@@ -101,6 +101,8 @@ SIGNATURES = {
     "epn_set_slab_bytes": (None, [c_sz]),
     "epn_get_slab_bytes": (c_sz, []),
     "epn_get_gemm_backend": (c_i, []),
+    "epn_set_fused_inter": (None, [c_i]),
+    "epn_get_fused_inter": (c_i, []),
 }
 
 _lib = None

@@ -33,7 +33,8 @@ enum KernelClass {
     KC_OTHER = 5,
     KC_SPLIT = 5,        // fp32 -> bf16 hi/lo split-tile conversion passes
     KC_NORM = 6,         // fused normalisation + leaky_relu
-    KC_COUNT = 7
+    KC_INTER_FUSED = 7,  // fused inter conv forward (gather + contraction + channel GEMM)
+    KC_COUNT = 8
 };
 
 // RAII: brackets the launches issued in its scope with a cudaEvent pair when profiling is on.

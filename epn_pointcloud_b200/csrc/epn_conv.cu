@@ -32,6 +32,17 @@ static int gemm_backend() {
     return v;
 }
 
+static std::atomic<int> g_fused{-1};
+
+static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused inter-conv kernel instead of grouping + GEMM
+    int v = g_fused.load();
+    if (v < 0) {
+        v = (getenv("EPN_FUSED") && strcmp(getenv("EPN_FUSED"), "1") == 0) ? 1 : 0;
+        g_fused.store(v);
+    }
+    return v;
+}
+
 static std::atomic<size_t> g_slab_bytes{0};
 
 static size_t slab_budget_bytes() {
@@ -214,8 +225,7 @@ static int gemm_dx(const float *W, int c_out, int ck, ColsView dout, int bc, lon
     // orientation: D[rows = (c,k), cols = (z,j)] so that an epilogue thread owns one (c,k) row and writes
     // runs of consecutive columns as 16-byte vectors (din is column-contiguous)
     const long long n = bc * cols;
-    static const int trn_max = getenv("EPN_DX_TRN") ? atoi(getenv("EPN_DX_TRN")) : 256;
-    const int trn = umma_trb_for((int)(n < trn_max ? n : trn_max));
+    const int trn = umma_trb_for((int)(n < 256 ? n : 256));
     SplitSrc src{dout.ptr, cols, dout.stride_z, 1, HUGE_Z, 0, dout.stride_k};
     int rc = launch_split_tiles(src, ws.tilesA, n, c_out, trn, s);
     if (rc) return rc;
@@ -270,6 +280,8 @@ EPN_API void epn_set_slab_bytes(size_t bytes) { g_slab_bytes.store(bytes < ((siz
 EPN_API size_t epn_get_slab_bytes(void) { return slab_budget_bytes(); }
 EPN_API void epn_set_gemm_backend(int simt) { g_backend.store(simt ? 1 : 0); }
 EPN_API int epn_get_gemm_backend(void) { return gemm_backend(); }
+EPN_API void epn_set_fused_inter(int on) { g_fused.store(on ? 1 : 0); }
+EPN_API int epn_get_fused_inter(void) { return fused_enabled(); }
 
 // ------------------------------------------------------------------ BasicSO3Conv
 EPN_API size_t epn_basic_conv_workspace_bytes(int b, int ck, int co, int pa) {
@@ -364,6 +376,16 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
+    if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && sp.pc == p && inter_fused_ok(c_in, c_out, p, nn, na, ks)) {
+        // one launch over every cloud: G stays in shared memory; kept tiles (training) keep the slab layout the
+        // weight-gradient pass expects
+        InterGeom g{xyz, centers, anchors, kernels, sigma};
+        const long long cols = (long long)p * na;
+        const int rc = launch_inter_fused(feats, idx, g, ws.tilesW, out, (long long)c_out * p * na, (long long)p * na, keep,
+                                          cdiv(ck, 32), cols, sp.bc, split_tiles_bytes((long long)sp.bc * cols, ck, 128), 0, p,
+                                          b, c_in, c_out, p_in, p, nn, na, ks, s);
+        if (rc != 1) return rc;
+    }
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int p0 = 0; p0 < p; p0 += sp.pc) {

@@ -303,6 +303,221 @@ umma_gemm_kernel(UmmaGemmParams p) {
     }
 }
 
+// ------------------------------------------------------------------ persistent GEMM
+// Same math and operand format as umma_gemm_kernel, scheduled differently: ONE CTA per SM walks over the output
+// tiles (m tile fastest, so neighbouring CTAs share the B tile in L2), the bulk-copy pipeline runs ahead across
+// tile boundaries, and the fp32 accumulator is double buffered in TMEM (2 x tmem_cols <= 512 columns) so the
+// epilogue of tile t (TMEM -> registers -> [shared staging ->] global) overlaps the main loop of tile t+1.
+// Per-tile fixed costs of the one-tile-per-CTA kernel (launch, TMEM allocation, barrier set-up, pipeline fill
+// and drain, store drain at exit) are paid once per SM; they dominated GEMMs with a short K loop and a large
+// output (dX = W^T dout: K = c_out, 128 KB of output per tile).
+__global__ void __launch_bounds__(192, 1)
+umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t stg_off) {
+    extern __shared__ uint8_t smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = p.k_blocks;
+    const int total = m_tiles * n_tiles;
+
+    const uint32_t a_bytes = (uint32_t)tile_bytes(TR_A), b_bytes = (uint32_t)tile_bytes(p.trb);
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+    const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t bars = base + p.stages * stage_bytes;  // full[stages], empty[stages], acc_full[2], acc_empty[2], slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (p.stages + s); };
+    auto acc_full = [&](int b) { return bars + 16u * p.stages + 8u * b; };
+    auto acc_empty = [&](int b) { return bars + 16u * p.stages + 16u + 8u * b; };
+    const uint32_t tmem_slot = bars + 16u * p.stages + 32u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full(b), 1);
+            mbar_init(acc_empty(b), 4);  // one arrival per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 2 * p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int tm = tile % m_tiles, tn = tile / m_tiles;
+                const uint8_t *a_src = p.A + (size_t)tm * nkb * a_bytes;
+                const uint8_t *b_src = p.B + (size_t)tn * nkb * b_bytes;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_arrive_expect_tx(full_bar(s), stage_bytes);
+                    bulk_g2s(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes, full_bar(s));
+                    bulk_g2s(base + s * stage_bytes + a_bytes, b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+            const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
+            int it = 0, t = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+                const int buf = t & 1;
+                mbar_wait(acc_empty(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * p.tmem_cols;
+                for (int i = 0; i < nkb; ++i, ++it) {
+                    const int s = it % p.stages;
+                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
+#pragma unroll
+                    for (int ks = 0; ks < KB / 16; ++ks) {
+                        const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
+                        const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
+                        const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
+                        const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
+                        mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (i | ks) != 0);
+                        mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1);
+                        mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1);
+                    }
+                    mma_commit(empty_bar(s));
+                }
+                mma_commit(acc_full(buf));
+            }
+        }
+    } else {
+        const bool col_split = p.cols_per_z < (long long)p.n_valid;
+        const uint32_t cpz = col_split ? (uint32_t)p.cols_per_z : 1u;
+        auto col_offset = [&](uint32_t col, long long stride_col) -> long long {
+            if (!col_split) return (long long)col * stride_col;
+            const uint32_t cz = col / cpz;
+            return (long long)cz * p.stride_cz + (long long)(col - cz * cpz) * stride_col;
+        };
+        const bool row_split = p.rows_per_z < (long long)p.m_valid;
+        auto row_offset = [&](long long r) -> long long {
+            if (!row_split) return r * p.stride_row;
+            const uint32_t rz = (uint32_t)r / (uint32_t)p.rows_per_z;
+            return (long long)rz * p.stride_z + (long long)((uint32_t)r - rz * (uint32_t)p.rows_per_z) * p.stride_row;
+        };
+        const int gw = p.trb < 128 ? p.trb : 128;  // columns per staged group
+        float *stg = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + stg_off) + (size_t)warp * 32 * (gw + 4);
+        int t = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+            const int tm = tile % m_tiles, tn = tile / m_tiles;
+            const int buf = t & 1;
+            mbar_wait(acc_full(buf), (uint32_t)(t >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)buf * p.tmem_cols + ((uint32_t)(warp * 32) << 16);
+            const long long row0 = (long long)tm * TR_A + warp * 32;
+            if (stg_off != 0u) {
+                // column-contiguous output (dX): stage 32 rows x gw columns, one asynchronous bulk store per row
+                for (int g0 = 0; g0 < p.trb; g0 += gw) {
+                    for (int cc = 0; cc < gw; cc += 32) {
+                        float v[32];
+                        tmem_ld_32x32(acc + (uint32_t)(g0 + cc), v);
+                        if (cc == 0) {  // the previous group's rows have left the staging buffer
+                            bulk_wait_read0();
+                            __syncwarp();
+                        }
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (cc + j < gw)
+                                *reinterpret_cast<float4 *>(stg + (size_t)lane * (gw + 4) + cc + j) =
+                                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                    if (g0 + gw >= p.trb) {  // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(buf));
+                    }
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    const long long colg = (long long)tn * p.trb + g0;
+                    const long long r = row0 + lane;
+                    if (r < p.m_valid && colg < p.n_valid) {
+                        const int ncols = (int)min((long long)min(gw, p.trb - g0), (long long)p.n_valid - colg);
+                        float *dst = p.out + row_offset(r) + col_offset((uint32_t)colg, 1);
+                        const float *src = stg + (size_t)lane * (gw + 4);
+                        const bool whole = !col_split || ((uint32_t)colg / cpz == (uint32_t)(colg + ncols - 1) / cpz);
+                        if (whole && (ncols & 3) == 0) {
+                            bulk_s2g(dst, smem_u32(src), (uint32_t)ncols * 4u);
+                        } else {
+                            for (int e = 0; e < ncols; ++e) p.out[row_offset(r) + col_offset((uint32_t)(colg + e), 1)] = src[e];
+                        }
+                    }
+                    bulk_commit();
+                }
+            } else {
+                const long long row = row0 + lane;
+                const bool row_ok = row < p.m_valid;
+                float *dst_row = p.out;
+                if (row_ok) dst_row += (row / p.rows_per_z) * p.stride_z + (row % p.rows_per_z) * p.stride_row;
+                for (int c0 = 0; c0 < p.trb; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(acc + (uint32_t)c0, v);
+                    if (c0 + 32 >= p.trb) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(buf));
+                    }
+                    const long long colb = (long long)tn * p.trb + c0;
+                    if (p.vec) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const long long col = colb + j;
+                            if (row_ok && c0 + j < p.trb && col < p.n_valid) {
+                                float *dst = dst_row + col_offset((uint32_t)col, 1);
+                                if (col + 3 < p.n_valid) {
+                                    *reinterpret_cast<float4 *>(dst) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                } else {
+                                    for (int e = 0; e < 4 && col + e < p.n_valid; ++e) dst[e] = v[j + e];
+                                }
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const long long col = colb + j;
+                            if (row_ok && c0 + j < p.trb && col < p.n_valid) {
+                                float *dst = dst_row + col_offset((uint32_t)col, p.stride_col);
+                                if (p.mode) atomicAdd(dst, v[j]);
+                                else *dst = v[j];
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (stg_off != 0u) bulk_wait_read0();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * p.tmem_cols);
+    }
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
 int umma_trb_for(int n_rows) {  // rows per B tile = UMMA N: multiple of 16, at most 256
     int t = (n_rows + 15) / 16 * 16;
     return t > 256 ? 256 : t;
@@ -328,8 +543,6 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     int stages = (int)((200 * 1024) / stage);
     if (stages > 4) stages = 4;
     if (trb <= 128 && stages > 3) stages = 3;  // 2 CTAs per SM
-    static const int st_small = getenv("EPN_DX_STAGES") ? atoi(getenv("EPN_DX_STAGES")) : 0;
-    if (st_small && trb <= 128 && K <= 256) stages = st_small;
     if (trb > 128) stages = 2;                 // 96 KB per CTA: 2 CTAs per SM (2 x 256 TMEM columns), the
                                                // epilogue of one overlaps the main loop of the other
     if (stages < 2) stages = 2;
@@ -361,8 +574,36 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
         set_error("umma_gemm: grid too large");
         return EPN_ERR_SHAPE;
     }
-    const size_t smem = (size_t)stages * stage + 128 + 16 * stages + 32;
     ProfScope prof(s, KC_GEMM);
+    static const int persistent_on = (getenv("EPN_GEMM_PERSISTENT") && atoi(getenv("EPN_GEMM_PERSISTENT")) == 0) ? 0 : 1;
+    const long long total_tiles = (long long)grid.x * grid.y;
+    // column-contiguous outputs (dX: short K loop, 128 KB of output per tile) run persistently: measured
+    // 264 -> 167 us per launch; the K-long forward GEMM streams better as two independent CTAs per SM
+    if (persistent_on && p.vec && split_k == 1 && total_tiles >= 2LL * sm_count() && total_tiles < (1LL << 31)) {
+        static bool attr2 = false;
+        if (!attr2) {
+            cudaError_t e = cudaFuncSetAttribute(umma_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+            if (e != cudaSuccess) {
+                set_error("umma_gemm_persistent_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+                return (int)e;
+            }
+            attr2 = true;
+        }
+        const int gw = trb < 128 ? trb : 128;
+        const size_t stg_bytes = p.vec ? (size_t)4 * 32 * (gw + 4) * sizeof(float) : 0;  // staged bulk-store epilogue (dX)
+        const size_t avail = (size_t)226 * 1024 - 512 - stg_bytes;
+        int pst = (int)(avail / stage);
+        if (pst > 8) pst = 8;
+        if (pst >= 2) {
+            p.stages = pst;
+            const size_t pipe = (((size_t)pst * stage + 16 * pst + 64) + 127) & ~(size_t)127;
+            const size_t smem_p = 128 + pipe + stg_bytes;
+            const int ctas = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
+            umma_gemm_persistent_kernel<<<ctas, 192, smem_p, s>>>(p, (int)grid.x, (int)grid.y, stg_bytes ? (uint32_t)pipe : 0u);
+            return check_launch("umma_gemm_persistent_kernel");
+        }
+    }
+    const size_t smem = (size_t)stages * stage + 128 + 16 * stages + 32;
     umma_gemm_kernel<<<grid, 192, smem, s>>>(p);
     return check_launch("umma_gemm_kernel");
 }

@@ -443,6 +443,11 @@ def set_gemm_backend(name):
     _lib.lib().epn_set_gemm_backend({"umma": 0, "simt": 1}[name])
 
 
+def set_fused_inter(on):
+    """True: InterSO3Conv forward runs as ONE fused kernel; False (default): grouping kernel + GEMM kernel."""
+    _lib.lib().epn_set_fused_inter(1 if on else 0)
+
+
 # ------------------------------------------ drop-in namespaces for vgtk.cuda.*
 grouping = types.SimpleNamespace(ball_query=ball_query, furthest_point_sampling=furthest_point_sampling)
 gathering = types.SimpleNamespace(gather_points_forward=gather_points_forward,

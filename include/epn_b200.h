@@ -213,6 +213,13 @@ void epn_set_gemm_backend(int simt);
 void epn_set_slab_bytes(size_t bytes);
 size_t epn_get_slab_bytes(void);
 int epn_get_gemm_backend(void);
+/* InterSO3Conv forward schedule on the tensor-core engine: 0 (default) = grouping kernel writing operand tiles
+ * followed by the GEMM kernel; 1 (or EPN_FUSED=1) = ONE fused kernel (gather + kernel weights + spatial
+ * contraction feeding the channel GEMM from shared memory; replaces the op chain
+ * vgtk/vgtk/so3conv/functional.py:118-218 -> spconv/functional.py:361-390 -> so3conv/modules.py:48-55).
+ * Both give the same results (tests); the two-kernel schedule is the faster one on the B200 today. */
+void epn_set_fused_inter(int on);
+int epn_get_fused_inter(void);
 
 #ifdef __cplusplus
 }

@@ -439,6 +439,36 @@ def test_umma_engine_matches_simt_inter(E, both_backends, c_in, c_out, p_in, str
         assert rel_err(a, b_) < 3e-5, name
 
 
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,b", [
+    (4, 8, 96, 2, 16, 2), (8, 40, 64, 1, 16, 3), (64, 64, 512, 1, 16, 2), (64, 128, 512, 2, 32, 2), (128, 128, 256, 1, 16, 7),
+    (128, 256, 256, 2, 32, 2), (256, 256, 128, 1, 16, 2), (256, 256, 128, 2, 32, 3), (12, 16, 50, 1, 5, 2),
+])
+def test_fused_inter_conv_matches_two_kernel_schedule(E, c_in, c_out, p_in, stride, nn_, b):
+    """The fused kernel (gather + contraction + GEMM from shared memory) against the grouping-kernel + GEMM-kernel
+    schedule of the same engine: same operand rounding, so the outputs agree to fp32 summation order; the kept
+    operand tiles it writes for the weight gradient must give the same dW; inference (no kept tiles) too."""
+    conv = _layer(E, c_in, c_out, stride, nn_, 0.45, 0.1)
+    xyz = sphere(b, p_in, 23).to(DEV)
+    res = {}
+    from epn_pointcloud_b200 import _lib
+    default = _lib.lib().epn_get_fused_inter()
+    try:
+        for fused in (False, True):
+            E.ops.set_fused_inter(fused)
+            f = torch.randn(b, c_in, p_in, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(7)).requires_grad_(True)
+            conv.zero_grad()
+            _, _, _, y = conv(E.SphericalPointCloud(xyz, f, None))
+            r = torch.randn(y.feats.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(8))
+            (y.feats * r).sum().backward()
+            with torch.no_grad():
+                _, _, _, y2 = conv(E.SphericalPointCloud(xyz, f.detach(), None))
+            res[fused] = (y.feats.detach(), f.grad.detach(), conv.basic_conv.W.grad.detach().clone(), y2.feats)
+    finally:
+        E.ops.set_fused_inter(bool(default))
+    for a, b_, name in zip(res[True], res[False], ("out", "dfeats", "dW", "out_no_grad")):
+        assert rel_err(a, b_) < 2e-6, name
+
+
 @pytest.mark.parametrize("c_in,c_out,p", [(4, 8, 32), (64, 64, 512), (128, 128, 256), (256, 256, 128), (5, 300, 17)])
 def test_umma_engine_matches_simt_intra(E, both_backends, c_in, c_out, p):
     torch.manual_seed(0)
