@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="clouds per GPU per step (weak scaling)")
     ap.add_argument("--ref-batch", type=int, default=2, help="clouds per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-step", action="store_true",
                     help="run warm-up, then ONE step inside cudaProfilerStart/Stop and exit (for ncu)")
     args = ap.parse_args()
@@ -201,7 +202,7 @@ def main():
     import epn_pointcloud_b200  # noqa: F401
     from epn_pointcloud_b200 import _lib
     from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
-    from epn_pointcloud_b200.parallel import FlatGradSync
+    from epn_pointcloud_b200.parallel import FlatGradSync, GraphedTrainStep
 
     assert torch.cuda.is_available(), "bench.py measures the CUDA path; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -222,7 +223,7 @@ def main():
     x_stage = torch.empty_like(x_dev)
     labels = synthetic_labels(B, 2 + rank).to(dev)
 
-    def step(x):
+    def eager_step(x):
         sync.zero()
         logits, _ = model(x)
         loss = torch.nn.functional.cross_entropy(logits, labels)
@@ -230,6 +231,13 @@ def main():
         sync.all_reduce_mean()
         opt.step()
         return loss
+
+    step, graphed = eager_step, None
+    if not args.no_graph and not args.profile_step:
+        # the public training-step helper: forward + loss + backward replayed from ONE CUDA graph
+        graphed = GraphedTrainStep(model, lambda out, lab: torch.nn.functional.cross_entropy(out[0], lab), opt, sync,
+                                   x_dev, labels, warmup=args.warmup)
+        step = lambda x: graphed(x)  # noqa: E731
 
     def barrier():
         if world > 1:
@@ -264,6 +272,8 @@ def main():
         e1.record()
         barrier()
     launches = L.epn_launch_count() - n0
+    if graphed is not None:  # replayed launches are not seen by the host-side counter: counted once at capture
+        launches = graphed.launches_per_replay * args.steps
     ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms * 1e-3)
 
@@ -282,7 +292,7 @@ def main():
     #      launching stream) -> roofline of the dominant kernel class
     import ctypes
     L.epn_profile_enable(1)
-    step(x_dev)
+    eager_step(x_dev)
     torch.cuda.synchronize()
     L.epn_profile_enable(0)
     ms_c = (ctypes.c_double * len(CLASSES))()
@@ -328,6 +338,7 @@ def main():
             "config": {"workload": "ModelNet40 cls network (7 inter + 7 intra SPConv layers + head) fwd+bwd+Adam, "
                                    "1024 pts, 60 anchors (BASELINE configs[1])", "clouds_per_gpu": B, "global_batch": B * world,
                        "parallelism": "batch-sharded x%d, one flat-gradient all-reduce" % world,
+                       "launch": "eager" if graphed is None else "CUDA graph replay (fwd+loss+bwd), eager all-reduce + Adam",
                        "l2": "no explicit flush: every step streams several GB of activations through the 126 MB L2"},
             "e2e": {"value": e2e, "unit": "clouds/s", "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

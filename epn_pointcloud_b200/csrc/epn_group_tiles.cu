@@ -52,7 +52,7 @@ inter_group_tiles_kernel(const float *__restrict__ feats, const int32_t *__restr
     const int a = tid % GT_LANES, grp = tid / GT_LANES;
     const int k0 = grp * KG;
     const bool a_ok = a < NA;
-    const int aa = a_ok ? a : 0;
+    const int aa = a_ok ? a : a - 4;  // dead lanes shadow a live lane of their own warp (broadcast, no bank conflict)
     const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
     const float *F = feats ? feats + (size_t)z * c * p_in * NA : nullptr;
 

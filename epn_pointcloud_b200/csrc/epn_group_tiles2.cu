@@ -145,7 +145,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     const int a = tid % SC_LANES, grp = tid / SC_LANES;
     const int n0 = grp * SC_NB;
     const bool a_ok = a < NA;
-    const int aa = a_ok ? a : 0;
+    const int aa = a_ok ? a : a - 4;  // dead lanes shadow a live lane of their own warp (broadcast, no bank conflict)
     const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
     float *DF = dfeats + (size_t)z * c * p_in * NA;
 
