@@ -572,9 +572,19 @@ EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, con
                        (long long)p * na};
             ColsView slab{ws.slab, cols, n_slab};
             if (dfeats != nullptr) {
-                EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
-                EPN_TRY(launch_intra_group_bwd(ws.slab, cols, n_slab, p0, pc, intra_idx,
-                                               dfeats + (size_t)b0 * c_in * p * na, bc, c_in, p, na, kn, s));
+                // fused: dG = W^T . dout reduced through the inverse anchor permutations inside the GEMM epilogue
+                // (dG, 12x the size of dfeats, never reaches HBM); otherwise GEMM into the slab + gather kernel
+                int rc = 1;
+                if (gemm_backend() == 0 && pc == p && intra_dx_fused_ok(n_slab, p, na, kn) &&
+                    intra_dx_wt_bytes(c_in, c_out) <= (size_t)ck * n_slab * sizeof(float))
+                    rc = launch_umma_intra_dx(d.ptr, d.stride_z, d.stride_k, W, intra_idx, dfeats + (size_t)b0 * c_in * p * na,
+                                              ws.slab, ws.tilesA, bc, c_in, c_out, p, s);
+                if (rc != 0 && rc != 1) return rc;
+                if (rc == 1) {
+                    EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
+                    EPN_TRY(launch_intra_group_bwd(ws.slab, cols, n_slab, p0, pc, intra_idx,
+                                                   dfeats + (size_t)b0 * c_in * p * na, bc, c_in, p, na, kn, s));
+                }
             }
             const uint8_t *kept = keep;
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);

@@ -130,6 +130,12 @@ struct UmmaGemmParams {
     float *out;
     long long rows_per_z, stride_z, stride_row, stride_col, cols_per_z, stride_cz;
     int m_valid, n_valid, mode, split_k, vec;
+    // ep_kind 2 (intra conv data gradient): the tile is reduced through the inverse anchor permutations
+    // before it leaves the SM (see launch_umma_intra_dx)
+    int ep_kind = 0;
+    const int32_t *intra_idx = nullptr;  // [60][12]
+    float *dfeats = nullptr;             // [z][ch_total][pts_per_z][60]
+    int ch_total = 0, pts_per_z = 0;
 };
 
 __global__ void __launch_bounds__(192)
@@ -303,6 +309,8 @@ umma_gemm_kernel(UmmaGemmParams p) {
     }
 }
 
+constexpr int IDX_STR = 244;  // row stride (floats) of the whole-tile staging of the intra data-gradient epilogue
+
 // ------------------------------------------------------------------ persistent GEMM
 // Same math and operand format as umma_gemm_kernel, scheduled differently: ONE CTA per SM walks over the output
 // tiles (m tile fastest, so neighbouring CTAs share the B tile in L2), the bulk-copy pipeline runs ahead across
@@ -410,6 +418,16 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
         };
         const int gw = p.trb < 128 ? p.trb : 128;  // columns per staged group
         float *stg = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + stg_off) + (size_t)warp * 32 * (gw + 4);
+        // ep_kind 2: whole-tile staging S[128][IDX_STR] + the inverse anchor permutations inv[k][a']
+        float *S = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + stg_off);
+        int32_t *s_inv = reinterpret_cast<int32_t *>(S + 128 * IDX_STR);
+        if (p.ep_kind == 2) {
+            for (int i = threadIdx.x; i < 60 * 12; i += 128) {
+                const int a = i / 12, k = i - a * 12;
+                s_inv[k * 60 + p.intra_idx[i]] = a;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         int t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
             const int tm = tile % m_tiles, tn = tile / m_tiles;
@@ -418,7 +436,49 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)buf * p.tmem_cols + ((uint32_t)(warp * 32) << 16);
             const long long row0 = (long long)tm * TR_A + warp * 32;
-            if (stg_off != 0u) {
+            if (p.ep_kind == 2) {
+                // dfeats[z, ch, pt, a'] = sum_k dG[(ch,k), (pt, inv_k(a'))]: tile rows = 10 channels x 12 k (+8 dead),
+                // tile columns = 4 points x 60 anchors, so the whole reduction is tile-local
+                const int tid = threadIdx.x;  // = TMEM lane = tile row
+                for (int c0 = 0; c0 < 240; c0 += 32) {
+                    float v[32];
+                    tmem_ld_32x32(acc + (uint32_t)c0, v);
+                    if (c0 + 32 >= 240) {  // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acc_empty(buf));
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (c0 + j < 240)
+                            *reinterpret_cast<float4 *>(S + (size_t)tid * IDX_STR + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                // thread <-> two fixed tile columns (tid, tid + 120): their inverse-permuted source columns sit in
+                // registers, the 10 channels of the tile stream through (12 LDS + 12 FADD per output)
+                if (tid < 120) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int col = tid + h * 120, pt = col / 60, a2 = col - pt * 60;
+                        const long long gp = (long long)tn * 4 + pt;  // point index over (z, pt) of this launch
+                        if (gp * 60 >= p.n_valid) continue;
+                        int src[12];
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) src[k] = k * IDX_STR + pt * 60 + s_inv[k * 60 + a2];
+                        const long long zz = gp / p.pts_per_z, pp = gp - zz * p.pts_per_z;
+                        float *drow = p.dfeats + ((zz * p.ch_total + (long long)tm * 10) * p.pts_per_z + pp) * 60 + a2;
+                        const int nch = min(10, p.ch_total - tm * 10);
+                        for (int cl = 0; cl < nch; ++cl) {
+                            const float *sblk = S + (size_t)(cl * 12) * IDX_STR;
+                            float acc_v = 0.f;
+#pragma unroll
+                            for (int k = 0; k < 12; ++k) acc_v += sblk[src[k]];
+                            drow[(size_t)cl * p.pts_per_z * 60] = acc_v;
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // S is free for the next tile
+            } else if (stg_off != 0u) {
                 // column-contiguous output (dX): stage 32 rows x gw columns, one asynchronous bulk store per row
                 for (int g0 = 0; g0 < p.trb; g0 += gw) {
                     for (int cc = 0; cc < gw; cc += 32) {
@@ -497,7 +557,7 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                 }
             }
         }
-        if (stg_off != 0u) bulk_wait_read0();
+        if (stg_off != 0u && p.ep_kind != 2) bulk_wait_read0();
     }
     tc_fence_before();
     __syncthreads();
@@ -606,6 +666,91 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     const size_t smem = (size_t)stages * stage + 128 + 16 * stages + 32;
     umma_gemm_kernel<<<grid, 192, smem, s>>>(p);
     return check_launch("umma_gemm_kernel");
+}
+
+// ------------------------------------------------------------------ intra conv data gradient, fused
+// W^T operand with padded rows: tile t holds rows (cl*12 + k), cl < 10 channels (ch = t*10 + cl), + 8 zero rows;
+// K = c_out.  Element = W[o, ch*12 + k].
+__global__ void __launch_bounds__(256)
+intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_in, int c_out, int k_blocks) {
+    const int rt = blockIdx.x, kcg = blockIdx.y * 2 + (threadIdx.x >> 7), r = threadIdx.x & 127;
+    if (kcg >= k_blocks * (KB / 8)) return;
+    const int cl = r / 12, k = r - cl * 12, ch = rt * 10 + cl;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int o = kcg * 8 + i;
+        x[i] = (r < 120 && ch < c_in && o < c_out) ? __ldg(W + (size_t)o * c_in * 12 + ch * 12 + k) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    uint8_t *tile = dst + ((size_t)rt * k_blocks + (kcg >> 2)) * tile_bytes(TR_A);
+    *reinterpret_cast<uint4 *>(tile + (size_t)(kcg & 3) * TR_A * 16 + (size_t)r * 16) = hi;
+    *reinterpret_cast<uint4 *>(tile + part_bytes(TR_A) + (size_t)(kcg & 3) * TR_A * 16 + (size_t)r * 16) = lo;
+}
+
+size_t intra_dx_wt_bytes(int c_in, int c_out) { return (size_t)cdiv(c_in, 10) * cdiv(c_out, KB) * tile_bytes(TR_A); }
+size_t intra_dx_dout_bytes(long long n, int c_out) { return split_tiles_bytes(n, c_out, 240); }
+
+bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn) { return na == 60 && kn == 12 && p % 4 == 0 && n_cols % 240 == 0; }
+
+// dfeats[z, ch, pt, a'] = sum_{o,k} W[o, ch*12+k] * dout[z, o, pt, inv_k(a')]   for bc clouds (autograd of
+// IntraSO3Conv w.r.t. its input, vgtk/vgtk/so3conv/modules.py:197-200 + so3conv/functional.py:221-268).
+// wt_tiles / dout_tiles: scratch of intra_dx_wt_bytes / intra_dx_dout_bytes.  The grouped gradient
+// dG[(c,k), columns] (12x the size of dfeats) only ever exists as one TMEM accumulator tile per SM.
+int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
+                         const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
+                         int c_out, int p, cudaStream_t s) {
+    const long long n = (long long)bc * p * 60;
+    if (!intra_dx_fused_ok(n, p, 60, 12) || n >= (1LL << 31)) return 1;
+    const int k_blocks = cdiv(c_out, KB), m_tiles = cdiv(c_in, 10);
+    {
+        ProfScope prof(s, KC_SPLIT);
+        dim3 grid(m_tiles, cdiv(k_blocks * (KB / 8), 2));
+        intra_wt_tiles_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(wt_tiles), c_in, c_out, k_blocks);
+        int rc = check_launch("intra_wt_tiles_kernel");
+        if (rc) return rc;
+    }
+    SplitSrc src{dout, (long long)p * 60, dout_stride_z, 1, 1LL << 60, 0, dout_stride_o};
+    int rc = launch_split_tiles(src, dout_tiles, n, c_out, 240, s);
+    if (rc) return rc;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(umma_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+        if (e != cudaSuccess) {
+            set_error("umma_gemm_persistent_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr = true;
+    }
+    UmmaGemmParams q;
+    q.A = static_cast<const uint8_t *>(wt_tiles);
+    q.B = static_cast<const uint8_t *>(dout_tiles);
+    q.k_blocks = k_blocks;
+    q.trb = 240;
+    q.tmem_cols = 256;
+    q.out = nullptr;
+    q.rows_per_z = 1LL << 60; q.stride_z = 0; q.stride_row = 0; q.stride_col = 1; q.cols_per_z = 1LL << 60; q.stride_cz = 0;
+    q.m_valid = m_tiles * TR_A;
+    q.n_valid = (int)n;
+    q.mode = 0; q.split_k = 1; q.vec = 0;
+    q.ep_kind = 2;
+    q.intra_idx = intra_idx;
+    q.dfeats = dfeats;
+    q.ch_total = c_in;
+    q.pts_per_z = p;
+    const size_t stage = tile_bytes(TR_A) + tile_bytes(240);
+    const size_t stg_bytes = (size_t)128 * IDX_STR * sizeof(float) + 60 * 12 * sizeof(int32_t);
+    int pst = (int)(((size_t)226 * 1024 - 512 - stg_bytes) / stage);
+    if (pst > 8) pst = 8;
+    if (pst < 2) return 1;
+    q.stages = pst;
+    const size_t pipe = (((size_t)pst * stage + 16 * pst + 64) + 127) & ~(size_t)127;
+    const long long n_tiles = n / 240, total = (long long)m_tiles * n_tiles;
+    const int ctas = (int)(total < sm_count() ? total : sm_count());
+    ProfScope prof(s, KC_GEMM);
+    umma_gemm_persistent_kernel<<<ctas, 192, 128 + pipe + stg_bytes, s>>>(q, m_tiles, (int)n_tiles, (uint32_t)pipe);
+    return check_launch("umma_gemm_persistent_kernel(intra dX)");
 }
 
 }  // namespace epn
