@@ -31,7 +31,7 @@ import torch  # noqa: E402
 METRIC = "point-clouds/sec, ModelNet40 1024-pt 60-anchor SPConv fwd+bwd"
 N_POINTS, N_ANCHORS, KS, KN = 1024, 60, 24, 12
 CLASSES = ["index_ops", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group", "channel_gemm", "split_convert",
-           "norm_act"]
+           "norm_act", "inter_fused_fwd"]
 
 
 def synthetic_clouds(b, n, seed):

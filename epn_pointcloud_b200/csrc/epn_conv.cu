@@ -523,6 +523,16 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
             const int pc = p - p0 < sp.pc ? p - p0 : sp.pc;
             const long long cols = (long long)pc * na, n_slab = bc * cols;
             ColsView o{out + ((size_t)b0 * c_out * p + p0) * na, (long long)c_out * p * na, (long long)p * na};
+            if (grouped == nullptr && gemm_backend() == 0 && pc == p && intra_dx_fused_ok(n_slab, p, na, kn) &&
+                intra_dx_wt_bytes(c_out, c_in) <= (size_t)ck * n_slab * sizeof(float)) {
+                // inference (no operand tiles to keep for the weight gradient): Y_k = W_k . feats on the tensor cores,
+                // out = sum_k Y_k permuted, reduced in shared memory -- the 12x larger grouped tensor never exists
+                const float *fz = feats + (size_t)b0 * c_in * p * na;
+                const int rc = launch_umma_intra_dx(fz, (long long)c_in * p * na, (long long)p * na, W, intra_idx,
+                                                    out + (size_t)b0 * c_out * p * na, ws.slab, ws.tilesA, bc, c_in, c_out, p, 1, s);
+                if (rc == 0) continue;
+                if (rc != 1) return rc;
+            }
             void *tiles = keep ? keep : ws.tilesA;
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;
@@ -578,7 +588,7 @@ EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, con
                 if (gemm_backend() == 0 && pc == p && intra_dx_fused_ok(n_slab, p, na, kn) &&
                     intra_dx_wt_bytes(c_in, c_out) <= (size_t)ck * n_slab * sizeof(float))
                     rc = launch_umma_intra_dx(d.ptr, d.stride_z, d.stride_k, W, intra_idx, dfeats + (size_t)b0 * c_in * p * na,
-                                              ws.slab, ws.tilesA, bc, c_in, c_out, p, s);
+                                              ws.slab, ws.tilesA, bc, c_in, c_out, p, 0, s);
                 if (rc != 0 && rc != 1) return rc;
                 if (rc == 1) {
                     EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));

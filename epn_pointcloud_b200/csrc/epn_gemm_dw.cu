@@ -11,6 +11,8 @@
 // 1-KB pieces (64 n of one 8-kk group) of four adjacent forward tiles into a stage
 //     A stage = [part][kk group: 16][n: 64][8 kk]     SBO (8-kk group stride) = 1 KB, LBO (8-n group stride) = 128 B
 // and the MMA is issued with a_major = MN.  B = dout tiles (rows = o, K = n), K-major as everywhere else.
+#include <stdlib.h>
+
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
@@ -179,7 +181,8 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
     p.ck = ck;
     p.c_out = c_out;
     const int m_tiles = (ck + TR_A - 1) / TR_A, n_tiles = (c_out + trb - 1) / trb;
-    long long sk = (148LL * 3 + (long long)m_tiles * n_tiles - 1) / ((long long)m_tiles * n_tiles);
+    static const int waves = getenv("EPN_DW_WAVES") ? atoi(getenv("EPN_DW_WAVES")) : 3;
+    long long sk = (148LL * waves + (long long)m_tiles * n_tiles - 1) / ((long long)m_tiles * n_tiles);
     const long long maxk = p.units / 8 > 0 ? p.units / 8 : 1;
     if (sk > maxk) sk = maxk;
     if (sk > 65535) sk = 65535;

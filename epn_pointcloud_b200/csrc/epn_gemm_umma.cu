@@ -421,10 +421,11 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
         // ep_kind 2: whole-tile staging S[128][IDX_STR] + the inverse anchor permutations inv[k][a']
         float *S = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + stg_off);
         int32_t *s_inv = reinterpret_cast<int32_t *>(S + 128 * IDX_STR);
-        if (p.ep_kind == 2) {
+        if (p.ep_kind >= 2) {
             for (int i = threadIdx.x; i < 60 * 12; i += 128) {
                 const int a = i / 12, k = i - a * 12;
-                s_inv[k * 60 + p.intra_idx[i]] = a;
+                if (p.ep_kind == 2) s_inv[k * 60 + p.intra_idx[i]] = a;  // source anchor of (k, a') under the inverse
+                else s_inv[k * 60 + a] = p.intra_idx[i];                 // forward: source anchor of (k, a)
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
@@ -436,7 +437,7 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
             tc_fence_after();
             const uint32_t acc = tmem_base + (uint32_t)buf * p.tmem_cols + ((uint32_t)(warp * 32) << 16);
             const long long row0 = (long long)tm * TR_A + warp * 32;
-            if (p.ep_kind == 2) {
+            if (p.ep_kind >= 2) {
                 // dfeats[z, ch, pt, a'] = sum_k dG[(ch,k), (pt, inv_k(a'))]: tile rows = 10 channels x 12 k (+8 dead),
                 // tile columns = 4 points x 60 anchors, so the whole reduction is tile-local
                 const int tid = threadIdx.x;  // = TMEM lane = tile row
@@ -557,7 +558,7 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                 }
             }
         }
-        if (stg_off != 0u && p.ep_kind != 2) bulk_wait_read0();
+        if (stg_off != 0u && p.ep_kind < 2) bulk_wait_read0();
     }
     tc_fence_before();
     __syncthreads();
@@ -669,18 +670,20 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
 }
 
 // ------------------------------------------------------------------ intra conv data gradient, fused
-// W^T operand with padded rows: tile t holds rows (cl*12 + k), cl < 10 channels (ch = t*10 + cl), + 8 zero rows;
-// K = c_out.  Element = W[o, ch*12 + k].
+// Weight operand with padded rows: tile t holds rows (cl*12 + k), cl < 10 channels (ch = t*10 + cl), + 8 zero rows;
+// element (row (ch,k), K index j) = W[ch*s_ch + j*s_j + k].  Data gradient: ch = input channel, j = output channel
+// (s_ch = 12, s_j = c_in*12); forward: ch = output channel, j = input channel (s_ch = c_in*12, s_j = 12).
 __global__ void __launch_bounds__(256)
-intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_in, int c_out, int k_blocks) {
+intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int n_ch, int n_j, long long s_ch,
+                      long long s_j, int k_blocks) {
     const int rt = blockIdx.x, kcg = blockIdx.y * 2 + (threadIdx.x >> 7), r = threadIdx.x & 127;
     if (kcg >= k_blocks * (KB / 8)) return;
     const int cl = r / 12, k = r - cl * 12, ch = rt * 10 + cl;
     float x[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int o = kcg * 8 + i;
-        x[i] = (r < 120 && ch < c_in && o < c_out) ? __ldg(W + (size_t)o * c_in * 12 + ch * 12 + k) : 0.f;
+        const int j = kcg * 8 + i;
+        x[i] = (r < 120 && ch < n_ch && j < n_j) ? __ldg(W + (size_t)ch * s_ch + (size_t)j * s_j + k) : 0.f;
     }
     uint4 hi, lo;
     split8(x, hi, lo);
@@ -689,30 +692,37 @@ intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, in
     *reinterpret_cast<uint4 *>(tile + part_bytes(TR_A) + (size_t)(kcg & 3) * TR_A * 16 + (size_t)r * 16) = lo;
 }
 
-size_t intra_dx_wt_bytes(int c_in, int c_out) { return (size_t)cdiv(c_in, 10) * cdiv(c_out, KB) * tile_bytes(TR_A); }
-size_t intra_dx_dout_bytes(long long n, int c_out) { return split_tiles_bytes(n, c_out, 240); }
+size_t intra_dx_wt_bytes(int c_rows, int c_k) { return (size_t)cdiv(c_rows, 10) * cdiv(c_k, KB) * tile_bytes(TR_A); }
+size_t intra_dx_dout_bytes(long long n, int c_k) { return split_tiles_bytes(n, c_k, 240); }
 
 bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn) { return na == 60 && kn == 12 && p % 4 == 0 && n_cols % 240 == 0; }
 
-// dfeats[z, ch, pt, a'] = sum_{o,k} W[o, ch*12+k] * dout[z, o, pt, inv_k(a')]   for bc clouds (autograd of
-// IntraSO3Conv w.r.t. its input, vgtk/vgtk/so3conv/modules.py:197-200 + so3conv/functional.py:221-268).
-// wt_tiles / dout_tiles: scratch of intra_dx_wt_bytes / intra_dx_dout_bytes.  The grouped gradient
-// dG[(c,k), columns] (12x the size of dfeats) only ever exists as one TMEM accumulator tile per SM.
+// Anchor-permuted channel GEMM of the intra convolution, both directions, for bc clouds:
+//   forward == 0 (data gradient):  res[z, ch, pt, a'] = sum_{o,k} W[o, ch*12+k] * x[z, o, pt, inv_k(a')]
+//       (autograd of IntraSO3Conv w.r.t. its input; x = dout, c_rows = c_in, c_k = c_out)
+//   forward == 1:                  res[z, o, pt, a]   = sum_{c,k} W[o, c*12+k]  * x[z, c, pt, intra_idx[a,k]]
+//       (IntraSO3Conv.forward, vgtk/vgtk/so3conv/modules.py:197-200 + so3conv/functional.py:221-268;
+//        x = feats, c_rows = c_out, c_k = c_in)
+// wt_tiles / x_tiles: scratch of intra_dx_wt_bytes(c_rows, c_k) / intra_dx_dout_bytes(n, c_k).  The 12x larger
+// grouped tensor (G resp. dG) only ever exists as one TMEM accumulator tile per SM.
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, cudaStream_t s) {
+                         int c_out, int p, int forward, cudaStream_t s) {
     const long long n = (long long)bc * p * 60;
     if (!intra_dx_fused_ok(n, p, 60, 12) || n >= (1LL << 31)) return 1;
-    const int k_blocks = cdiv(c_out, KB), m_tiles = cdiv(c_in, 10);
+    const int c_rows = forward ? c_out : c_in, c_k = forward ? c_in : c_out;
+    const int k_blocks = cdiv(c_k, KB), m_tiles = cdiv(c_rows, 10);
     {
         ProfScope prof(s, KC_SPLIT);
         dim3 grid(m_tiles, cdiv(k_blocks * (KB / 8), 2));
-        intra_wt_tiles_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(wt_tiles), c_in, c_out, k_blocks);
+        intra_wt_tiles_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(wt_tiles), c_rows, c_k,
+                                                   forward ? (long long)c_in * 12 : 12LL, forward ? 12LL : (long long)c_in * 12,
+                                                   k_blocks);
         int rc = check_launch("intra_wt_tiles_kernel");
         if (rc) return rc;
     }
     SplitSrc src{dout, (long long)p * 60, dout_stride_z, 1, 1LL << 60, 0, dout_stride_o};
-    int rc = launch_split_tiles(src, dout_tiles, n, c_out, 240, s);
+    int rc = launch_split_tiles(src, dout_tiles, n, c_k, 240, s);
     if (rc) return rc;
     static bool attr = false;
     if (!attr) {
@@ -734,10 +744,10 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
     q.m_valid = m_tiles * TR_A;
     q.n_valid = (int)n;
     q.mode = 0; q.split_k = 1; q.vec = 0;
-    q.ep_kind = 2;
+    q.ep_kind = forward ? 3 : 2;  // 3: the permutations themselves, 2: their inverses
     q.intra_idx = intra_idx;
     q.dfeats = dfeats;
-    q.ch_total = c_in;
+    q.ch_total = c_rows;
     q.pts_per_z = p;
     const size_t stage = tile_bytes(TR_A) + tile_bytes(240);
     const size_t stg_bytes = (size_t)128 * IDX_STR * sizeof(float) + 60 * 12 * sizeof(int32_t);

@@ -122,12 +122,12 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
 
 // Intra conv data gradient with the inverse-permutation reduction fused into the GEMM epilogue (epn_gemm_umma.cu);
 // returns 1 if the shape is unsupported.
-size_t intra_dx_wt_bytes(int c_in, int c_out);
-size_t intra_dx_dout_bytes(long long n, int c_out);
+size_t intra_dx_wt_bytes(int c_rows, int c_k);
+size_t intra_dx_dout_bytes(long long n, int c_k);
 bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn);
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, cudaStream_t s);
+                         int c_out, int p, int forward, cudaStream_t s);
 
 // epn_gemm_dw.cu -- dW[c_out, ck] += dout . G straight from the forward operand tiles of a slab
 // (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles

@@ -117,8 +117,9 @@ class _InterSO3ConvFn(torch.autograd.Function):
         ctx.sigma = sigma
         ctx.has_feats = feats is not None
         ctx.save_for_backward(*( [feats] if feats is not None else [] ), W, xyz, centers, idx, anchors, kernels)
-        out, ctx.grouped = ops.inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W,
-                                                 keep_grouped=ctx.needs_input_grad[1])
+        keep = bool(ctx.needs_input_grad[1]) and torch.is_grad_enabled()  # inference keeps nothing
+        res = ops.inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W, keep_grouped=keep)
+        out, ctx.grouped = res if keep else (res, None)
         return out
 
     @staticmethod
@@ -139,7 +140,9 @@ class _IntraSO3ConvFn(torch.autograd.Function):
         feats = feats.contiguous()
         W = W.contiguous()
         ctx.save_for_backward(feats, W, intra_idx)
-        out, ctx.grouped = ops.intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=ctx.needs_input_grad[1])
+        keep = bool(ctx.needs_input_grad[1]) and torch.is_grad_enabled()  # inference keeps nothing
+        res = ops.intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=keep)
+        out, ctx.grouped = res if keep else (res, None)
         return out
 
     @staticmethod

@@ -486,6 +486,24 @@ def test_umma_engine_matches_simt_intra(E, both_backends, c_in, c_out, p):
         assert rel_err(a, b_) < 3e-5, name
 
 
+@pytest.mark.parametrize("c_in,c_out,p,b", [(4, 8, 32, 2), (64, 64, 512, 2), (128, 96, 256, 3), (256, 256, 128, 2), (30, 7, 20, 3)])
+def test_intra_forward_permuted_gemm_matches_grouped_schedule(E, both_backends, c_in, c_out, p, b):
+    """Inference forward of IntraSO3Conv (no operand tiles kept): Y_k = W_k.feats on tcgen05 + permuted sum in the
+    epilogue, against the training-mode schedule (gather into tiles + GEMM) and the fp32 SIMT engine."""
+    torch.manual_seed(1)
+    conv = E.IntraSO3Conv(c_in, c_out).to(DEV)
+    f = torch.randn(b, c_in, p, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(9))
+    both_backends("umma")
+    with torch.no_grad():
+        y_inf = conv(E.SphericalPointCloud(None, f, None)).feats
+    y_train = conv(E.SphericalPointCloud(None, f.clone().requires_grad_(True), None)).feats.detach()
+    both_backends("simt")
+    with torch.no_grad():
+        y_simt = conv(E.SphericalPointCloud(None, f, None)).feats
+    assert rel_err(y_inf, y_train) < 1e-5
+    assert rel_err(y_inf, y_simt) < 3e-5
+
+
 def test_umma_engine_many_slabs(E, both_backends, monkeypatch):
     """Force the slab scheduler to cut clouds into several point ranges (tile tails, row->(z,j) mapping)."""
     from epn_pointcloud_b200 import _lib
@@ -555,7 +573,10 @@ def test_dw_from_kept_forward_tiles_equals_recomputed(E, kind, c_in, c_out, p, n
     finally:
         L.epn_set_slab_bytes(old)
         E.ops.set_keep_grouped("auto")
-    assert torch.equal(res["on"][0], res["off"][0])          # same tiles, same GEMM: bit-identical forward
+    if kind == "intra":  # without kept tiles the forward is the permuted GEMM: same products, different summation order
+        assert rel_err(res["on"][0], res["off"][0]) < 3e-5   # the bar both hold against the fp32 SIMT engine
+    else:
+        assert torch.equal(res["on"][0], res["off"][0])      # same tiles, same GEMM: bit-identical forward
     assert rel_err(res["on"][1], res["off"][1]) < 5e-6       # same products, different summation order
     if res["on"][2] is not None:
         assert torch.equal(res["on"][2], res["off"][2]) or rel_err(res["on"][2], res["off"][2]) < 1e-6
