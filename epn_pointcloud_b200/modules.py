@@ -111,13 +111,14 @@ class _InterSO3ConvFn(torch.autograd.Function):
     kept tiles G is recomputed."""
 
     @staticmethod
-    def forward(ctx, feats, W, xyz, centers, idx, anchors, kernels, sigma):
+    def forward(ctx, feats, W, xyz, centers, idx, anchors, kernels, sigma, training=True):
         W = W.contiguous()
         feats = None if feats is None else feats.contiguous()
         ctx.sigma = sigma
         ctx.has_feats = feats is not None
         ctx.save_for_backward(*( [feats] if feats is not None else [] ), W, xyz, centers, idx, anchors, kernels)
-        keep = bool(ctx.needs_input_grad[1]) and torch.is_grad_enabled()  # inference keeps nothing
+        # `training` = grad mode of the CALLER (inside Function.forward grad mode is always off): inference keeps nothing
+        keep = bool(ctx.needs_input_grad[1]) and bool(training)
         res = ops.inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W, keep_grouped=keep)
         out, ctx.grouped = res if keep else (res, None)
         return out
@@ -131,16 +132,16 @@ class _InterSO3ConvFn(torch.autograd.Function):
         dfeats, dW = ops.inter_so3conv_bwd(dout.contiguous(), feats, xyz, centers, idx, anchors, kernels, ctx.sigma, W,
                                            need_dfeats=need_df, need_dw=ctx.needs_input_grad[1], grouped=ctx.grouped)
         ctx.grouped = None
-        return dfeats, dW, None, None, None, None, None, None
+        return dfeats, dW, None, None, None, None, None, None, None
 
 
 class _IntraSO3ConvFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, W, intra_idx):
+    def forward(ctx, feats, W, intra_idx, training=True):
         feats = feats.contiguous()
         W = W.contiguous()
         ctx.save_for_backward(feats, W, intra_idx)
-        keep = bool(ctx.needs_input_grad[1]) and torch.is_grad_enabled()  # inference keeps nothing
+        keep = bool(ctx.needs_input_grad[1]) and bool(training)  # see _InterSO3ConvFn
         res = ops.intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=keep)
         out, ctx.grouped = res if keep else (res, None)
         return out
@@ -151,7 +152,7 @@ class _IntraSO3ConvFn(torch.autograd.Function):
         dfeats, dW = ops.intra_so3conv_bwd(dout.contiguous(), feats, intra_idx, W, ctx.needs_input_grad[0],
                                            ctx.needs_input_grad[1], grouped=ctx.grouped)
         ctx.grouped = None
-        return dfeats, dW, None
+        return dfeats, dW, None, None
 
 
 # ------------------------------------------------------------------- modules
@@ -215,7 +216,7 @@ class InterSO3Conv(nn.Module):
                 inter_w = LazyInterW(xyz, new_xyz, inter_idx, self.anchors, self.kernels, self.sigma)
         if isinstance(inter_w, LazyInterW):
             out = _InterSO3ConvFn.apply(feats, W, inter_w.xyz, inter_w.centers, inter_idx, inter_w.anchors,
-                                        inter_w.kernels, inter_w.sigma)
+                                        inter_w.kernels, inter_w.sigma, torch.is_grad_enabled())
         else:  # caller supplied a materialised weight tensor: honour it (unfused op-surface path)
             grouped = L.inter_zpconv_grouping_naive(inter_idx, inter_w, x.feats)
             out = self.basic_conv(grouped)
@@ -244,5 +245,5 @@ class IntraSO3Conv(nn.Module):
         module._intra_idx32.copy_(module.intra_idx.to(torch.int32))
 
     def forward(self, x):
-        feats = _IntraSO3ConvFn.apply(x.feats, self.basic_conv.W, self._intra_idx32)
+        feats = _IntraSO3ConvFn.apply(x.feats, self.basic_conv.W, self._intra_idx32, torch.is_grad_enabled())
         return SphericalPointCloud(x.xyz, feats, self.anchors)

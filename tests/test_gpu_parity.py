@@ -500,7 +500,7 @@ def test_intra_forward_permuted_gemm_matches_grouped_schedule(E, both_backends, 
     both_backends("simt")
     with torch.no_grad():
         y_simt = conv(E.SphericalPointCloud(None, f, None)).feats
-    assert rel_err(y_inf, y_train) < 1e-5
+    assert rel_err(y_inf, y_train) < 3e-5   # two accumulation orders of the same products (K = 12*c_in vs 12 x K = c_in)
     assert rel_err(y_inf, y_simt) < 3e-5
 
 
