@@ -190,12 +190,17 @@ class BasicSO3ConvBlock(nn.Module):
 
 
 # --------------------------------------------------------- backbone arithmetic
-def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
-                        mlps=((64, 64), (128, 128), (256, 256), (256,)), strides=(2, 2, 2, 2),
-                        initial_radius_ratio=0.2, sampling_ratio=0.4, sampling_density=0.5,
-                        kernel_multiplier=2, input_radius=1.0, sigma_ratio=0.5, xyz_pooling=None):
-    """Layer hyper-parameters of the ModelNet40 classification backbone
-    (cls_so3net_pn.py:41-150): per-layer radius / sigma / neighbour count / stride."""
+def backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
+                    mlps=((64, 64), (128, 128), (256, 256), (256,)), strides=(2, 2, 2, 2),
+                    initial_radius_ratio=0.2, sampling_ratio=0.4, sampling_density=0.5,
+                    kernel_multiplier=2, input_radius=1.0, sigma_ratio=0.5, xyz_pooling=None,
+                    norm="BatchNorm2d", sigma_rule="double", scale_first_neighbor=False):
+    """Layer hyper-parameters (per-layer radius / sigma / neighbour count / stride) of the three shipped
+    backbones, i.e. the arithmetic of the reference's `build_model` functions:
+      cls (cls_so3net_pn.py:41-150):  norm="BatchNorm2d", sigma doubles per block;
+      reg (reg_so3net.py:54-171):     no norm key (InstanceNorm2d default), sigma doubles per block;
+      inv (inv_so3net_pn.py:43-163):  no norm key, sigma multiplied by the block's stride (:98-100), first layer's
+                                      neighbour count scaled by input_num/1024 (:112-113)."""
     strides = list(strides)
     na = kanchor
     if input_num > 1024:
@@ -208,7 +213,7 @@ def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
     radii = [r * input_radius for r in radius_ratio]
     weighted_sigma = [sigma_ratio * radii[0] ** 2]
     for i in range(len(strides)):
-        weighted_sigma.append(weighted_sigma[i] * 2)
+        weighted_sigma.append(weighted_sigma[i] * (2 if sigma_rule == "double" else strides[i]))
     backbone = []
     dim_in = 1
     for i, block in enumerate(mlps):
@@ -217,6 +222,8 @@ def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
             lazy_sample = i != 0 or j != 0
             stride_conv = i == 0 or xyz_pooling != "stride"
             neighbor = int(sampling_ratio * num_centers[i] * radius_ratio[i] ** (1 / sampling_density))
+            if scale_first_neighbor and i == 0 and j == 0:
+                neighbor *= int(input_num / 1024)
             if j == 0:
                 inter_stride = strides[i]
                 nidx = i if i == 0 else i + 1
@@ -225,16 +232,21 @@ def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0,
             else:
                 inter_stride = 1
                 nidx = i + 1
-            block_param.append({
-                "type": "inter_block" if na < 60 else "separable_block",
-                "args": {"dim_in": dim_in, "dim_out": dim_out, "kernel_size": 1, "stride": inter_stride,
-                         "radius": radii[nidx], "sigma": weighted_sigma[nidx], "n_neighbor": neighbor,
-                         "lazy_sample": lazy_sample, "dropout_rate": dropout_rate, "multiplier": kernel_multiplier,
-                         "activation": "leaky_relu", "pooling": xyz_pooling, "kanchor": na, "norm": "BatchNorm2d"},
-            })
+            args = {"dim_in": dim_in, "dim_out": dim_out, "kernel_size": 1, "stride": inter_stride,
+                    "radius": radii[nidx], "sigma": weighted_sigma[nidx], "n_neighbor": neighbor,
+                    "lazy_sample": lazy_sample, "dropout_rate": dropout_rate, "multiplier": kernel_multiplier,
+                    "activation": "leaky_relu", "pooling": xyz_pooling, "kanchor": na}
+            if norm is not None:
+                args["norm"] = norm
+            block_param.append({"type": "inter_block" if na != 60 else "separable_block", "args": args})
             dim_in = dim_out
         backbone.append(block_param)
     return backbone
+
+
+def cls_backbone_params(input_num=1024, kanchor=60, dropout_rate=0.0, **kw):
+    """ModelNet40 classification backbone (cls_so3net_pn.py:41-150)."""
+    return backbone_params(input_num, kanchor, dropout_rate, **kw)
 
 
 class SO3ConvBackbone(nn.Module):

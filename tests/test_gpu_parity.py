@@ -698,3 +698,55 @@ def test_full_cls_model_trains_one_step(E):
     torch.nn.functional.cross_entropy(logits, torch.tensor([3, 17], device=DEV)).backward()
     missing = [n for n, p in model.named_parameters() if p.grad is None or not bool(torch.isfinite(p.grad).all())]
     assert missing == []
+
+
+# ------------------------------------------------- the other two shipped models (8 f2): 3DMatch, rotation
+def test_inv_model_vs_reference_golden(E):
+    """InvSO3ConvModel (inv_so3net_pn.py:15-41: backbone + InvOutBlockMVD) with the reference's weights on the
+    reference's input: descriptor and anchor attention (reduced widths; K = 64/32 neighbours, InstanceNorm blocks)."""
+    from epn_pointcloud_b200.heads import InvSO3ConvModel
+    g = load_golden("inv_model_small")
+    model = InvSO3ConvModel(g["params"]).to(DEV).train()
+    model.load_state_dict(g.state_dict(), strict=True)
+    with torch.no_grad():
+        desc, attn = model(g["pc"].to(DEV))
+    assert desc.shape == g["desc"].shape and attn.shape == g["attn"].shape
+    assert rel_err(desc, g["desc"]) < 2e-4 and rel_err(attn, g["attn"]) < 2e-4
+
+
+def test_reg_model_vs_reference_golden(E):
+    """RegSO3ConvModel (reg_so3net.py:16-52: shared backbone over (source, target) + RelSO3OutBlockR): anchor-pair
+    confidence [nb, 60, 60] and quaternion residuals [nb, 4, 60, 60]."""
+    from epn_pointcloud_b200.heads import RegSO3ConvModel
+    g = load_golden("reg_model_small")
+    model = RegSO3ConvModel(g["params"]).to(DEV).train()
+    model.load_state_dict(g.state_dict(), strict=True)
+    with torch.no_grad():
+        conf, quats = model(g["pairs"].to(DEV))
+    assert conf.shape == g["conf"].shape and quats.shape == g["quats"].shape
+    assert rel_err(conf, g["conf"]) < 2e-4 and rel_err(quats, g["quats"]) < 2e-4
+
+
+@pytest.mark.parametrize("which", ["inv", "reg"])
+def test_full_size_inv_reg_models_train_one_step(E, which):
+    """BASELINE configs[2]/[3] shapes: the full-size rotation (1024 pts, 1 pair) and 3DMatch (2048 pts, K=128 first
+    layer) networks run forward + backward; every parameter receives a finite gradient."""
+    from epn_pointcloud_b200 import heads
+    torch.manual_seed(0)
+    if which == "inv":
+        model = heads.InvSO3ConvModel(heads.inv_model_params(2048, 60)).to(DEV).train()
+        d = torch.randn(1, 2048, 3, generator=torch.Generator().manual_seed(5))
+        pc = (0.4 * d / d.norm(dim=2, keepdim=True) * torch.rand(1, 2048, 1) ** (1 / 3)).to(DEV)
+        desc, _ = model(pc)
+        assert desc.shape == (1, 64)
+        loss = desc.square().sum() + desc[:, 0].sum()
+    else:
+        model = heads.RegSO3ConvModel(heads.reg_model_params(1024, 60)).to(DEV).train()
+        src = sphere(1, 1024, 78).permute(0, 2, 1).contiguous()
+        pairs = torch.stack([src, src.flip(2)], 1).to(DEV)
+        conf, quats = model(pairs)
+        assert conf.shape == (1, 60, 60) and quats.shape == (1, 4, 60, 60)
+        loss = (conf * quats[:, 0]).sum() + quats.square().mean()
+    loss.backward()
+    missing = [n for n, p in model.named_parameters() if p.grad is None or not bool(torch.isfinite(p.grad).all())]
+    assert missing == []

@@ -196,3 +196,22 @@ def test_backbone_small_port():
     xyz, out = TP.backbone_forward(g["pc"], layers)
     assert torch.equal(xyz, g["out_xyz"])
     assert rel_err(out, g["out"]) < 1e-4
+
+
+def test_inv_and_reg_model_arithmetic_and_state_dicts_match_reference():
+    """The layer arithmetic (radius / sigma / neighbour count / stride per layer) and every state-dict key and
+    shape of the full-size 3DMatch (2048 pts) and rotation (1024 pts) models equal what the reference's own
+    build_model produced (tests/golden/model_params_inv_reg.json, oracle/make_golden_models.py)."""
+    import json
+    import os
+    from epn_pointcloud_b200 import heads
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_params_inv_reg.json")))
+    for name, params, cls in (("inv", heads.inv_model_params(2048, 60), heads.InvSO3ConvModel),
+                              ("reg", heads.reg_model_params(1024, 60), heads.RegSO3ConvModel)):
+        assert json.loads(json.dumps(params["backbone"])) == g[name]
+        assert params["outblock"] == g[name + "_outblock"]
+        model = cls(params)
+        shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+        ref = g[name + "_state_shapes_all"]
+        assert {k: v for k, v in shapes.items() if not k.endswith("_intra_idx32")} == ref
+        assert sum(p.numel() for p in model.parameters()) == g[name + "_n_params"]
