@@ -43,6 +43,13 @@ static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused
     return v;
 }
 
+// Inter grouping with the bf16 split in registers + permuted K order (epn_group_direct.cu); EPN_DIRECT=0 keeps the
+// staging-tile kernel.  Forward and backward must agree, so the decision is a pure function of the call's shape.
+static bool inter_direct(const float *feats, int c_in, int nn, int na, int ks) {
+    static const int on = (getenv("EPN_DIRECT") && strcmp(getenv("EPN_DIRECT"), "0") == 0) ? 0 : 1;
+    return on && gemm_backend() == 0 && !fused_enabled() && inter_group_direct_ok(feats, c_in, nn, na, ks);
+}
+
 static std::atomic<size_t> g_slab_bytes{0};
 
 static size_t slab_budget_bytes() {
@@ -140,9 +147,13 @@ struct ColsView {
 
 constexpr long long HUGE_Z = 1LL << 60;
 
-static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s) {
+static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s,
+                        bool kperm = false) {
     if (gemm_backend() != 0) return 0;
-    if (fwd) {
+    if (fwd && kperm) {
+        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), s);
+        if (rc) return rc;
+    } else if (fwd) {
         SplitSrc src{W, HUGE_Z, 0, ck, HUGE_Z, 0, 1};
         int rc = launch_split_tiles(src, ws.tilesW, c_out, ck, umma_trb_for(c_out), s);
         if (rc) return rc;
@@ -174,13 +185,13 @@ static int gemm_fwd_tiles(const void *tilesA, int c_out, int ck, int bc, long lo
 
 // dW(c_out x ck) += dout . G with G = the forward operand tiles of this slab (rows = (z,j) columns, K = ck)
 static int gemm_dw_grouped(const void *grouped, ColsView dout, int c_out, int ck, int bc, long long cols, float *dW,
-                           const Workspace &ws, cudaStream_t s) {
+                           const Workspace &ws, cudaStream_t s, int kperm = 0) {
     const long long n = bc * cols;
     const int trb = umma_trb_for(c_out);
     SplitSrc sb{dout.ptr, HUGE_Z, 0, dout.stride_k, cols, dout.stride_z, 1};
     int rc = launch_split_tiles(sb, ws.tilesB, c_out, n, trb, s);
     if (rc) return rc;
-    return launch_umma_dw(grouped, ws.tilesB, ck, c_out, n, trb, dW, s);
+    return launch_umma_dw(grouped, ws.tilesB, ck, c_out, n, trb, dW, kperm, s);
 }
 
 // dW(c_out x ck) += dout . G^T with G^T already in ws.tilesA (rows = ck, K = (z,j) columns)
@@ -375,7 +386,8 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
-    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
+    const bool kperm = inter_direct(feats, c_in, nn, na, ks);
+    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm));
     if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && sp.pc == p && inter_fused_ok(c_in, c_out, p, nn, na, ks)) {
         // one launch over every cloud: G stays in shared memory; kept tiles (training) keep the slab layout the
         // weight-gradient pass expects
@@ -397,7 +409,11 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             void *tiles = keep ? keep : ws.tilesA;  // kept tiles: every slab has its own region
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;  // 0: the grouping kernel wrote the operand tiles itself
-            if (gemm_backend() == 0) {
+            if (kperm) {
+                direct = launch_inter_group_direct(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cdiv(ck, 32), cols, p0, pc, bc,
+                                                   c_in, p_in, p, nn, na, ks, s);
+                if (direct != 0) return direct == 1 ? EPN_ERR_SHAPE : direct;
+            } else if (gemm_backend() == 0) {
                 direct = launch_inter_group_tiles(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cdiv(ck, 32), 0, cols, 0,
                                                   p0, pc, bc, c_in, p_in, p, nn, na, ks, s);
                 if (direct != 0 && direct != 1) return direct;
@@ -465,8 +481,8 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
             const uint8_t *kept = keep;
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             if (dW != nullptr && kept != nullptr) {
-                // dW += dout . G with G = the operand tiles the forward kept
-                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s));
+                // dW += dout . G with G = the operand tiles the forward kept (K possibly in the permuted order)
+                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s, inter_direct(feats, c_in, nn, na, ks) ? 1 : 0));
             } else if (dW != nullptr) {
                 // dW += dout . G^T with G recomputed
                 const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;

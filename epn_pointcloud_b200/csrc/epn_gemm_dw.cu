@@ -31,7 +31,7 @@ struct DwParams {
     int g_k_blocks, b_k_blocks, units, trb, stages, split_k;
     uint32_t tmem_cols;
     float *dW;
-    int ck, c_out;
+    int ck, c_out, kperm;
 };
 
 __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
     } else {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
-        const int kk = blockIdx.x * TR_A + warp * 32 + lane;  // lanes <-> consecutive kk: coalesced REDs per o
+        const int kk_t = blockIdx.x * TR_A + warp * 32 + lane;  // lanes <-> consecutive tile rows
+        const int kk = (p.kperm && kk_t < p.ck) ? inter_kperm_inv(kk_t) : kk_t;  // row of dW^T in the weight's own order
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
 
 // G_tiles: forward operand tiles of one slab (n rows, n % 128 == 0, K = ck); B_tiles: dout tiles (rows = c_out, K = n)
 int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, long long n, int trb, float *dW,
-                   cudaStream_t s) {
+                   int kperm, cudaStream_t s) {
     if (n % 128 != 0 || n / UNIT >= (1LL << 31)) {
         set_error("umma_dw: n must be a multiple of 128");
         return EPN_ERR_SHAPE;
@@ -180,6 +181,7 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
     p.dW = dW;
     p.ck = ck;
     p.c_out = c_out;
+    p.kperm = kperm;
     const int m_tiles = (ck + TR_A - 1) / TR_A, n_tiles = (c_out + trb - 1) / trb;
     static const int waves = getenv("EPN_DW_WAVES") ? atoi(getenv("EPN_DW_WAVES")) : 3;
     long long sk = (148LL * waves + (long long)m_tiles * n_tiles - 1) / ((long long)m_tiles * n_tiles);

@@ -1,0 +1,235 @@
+// Inter grouping stage, K <= 16 neighbours, with the bf16 hi/lo split done IN REGISTERS.
+//
+//   G[(c,k), (z,p,a)] = sum_n w(p,a,k,n) * feats[z, c, idx[z,p,n], a]      (spconv/functional.py:361-390,
+//   w(p,a,k,n) = relu(1 - |x_idx - x_p - R_a kappa_k|^2 / sigma)             so3conv/functional.py:180-218)
+//
+// Same mapping as inter_group_tiles_kernel<16,6,8,60> (one CTA per output point, lane <-> anchor, warp pair <->
+// 6 kernel points, weights in registers as fp32x2 pairs, bulk-copy gather of the neighbour rows), but the fp32
+// staging tile and the separate conversion pass are gone (they were 36 % of that kernel's instructions): the
+// operand tiles use a PERMUTED K order chosen so that the 24 values a thread produces for 4 consecutive
+// channels are three whole 8-wide K chunks,
+//     K'(c, k) = (c/4)*96 + (k/6)*24 + (c%4)*6 + (k%6),
+// which it converts to bf16 hi/lo pairs as they leave the FMA loop and stores as 16-byte pieces (a warp writes
+// 512 contiguous bytes of a tile).  The order of the K dimension is internal to the engine: the weight tiles of
+// the forward GEMM are built in the same order and the weight-gradient GEMM un-permutes its output rows
+// (inter_kperm()).
+#include "epn_internal.cuh"
+#include "epn_umma.cuh"
+
+namespace epn {
+using namespace umma;
+
+namespace {
+constexpr int GD_LANES = 64, GD_KS = 24, GD_NN = 16, GD_KG = 6, GD_CCH = 8, GD_NA = 60;
+constexpr int GD_THR = GD_LANES * (GD_KS / GD_KG);  // 256
+
+__global__ void __launch_bounds__(GD_THR, 2)
+inter_group_direct_kernel(const float *__restrict__ feats, const int32_t *__restrict__ idx, InterGeom g,
+                          uint8_t *__restrict__ tiles, int k_blocks, long long cols_per_z, int c, int p_in, int p, int nn,
+                          int p_off) {
+    constexpr int NN = GD_NN, KG = GD_KG, CCH = GD_CCH, NA = GD_NA, NTHR = GD_THR;
+    extern __shared__ __align__(16) float s_dyn[];
+    float *s_g = s_dyn;                                            // [NN][3]  unique neighbour offsets
+    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]     unique neighbour indices
+    float *s_mult = s_dyn + NN * 4;                                // [NN]     their multiplicities
+    int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     the ball-query row as stored
+    float *Fs = s_dyn + NN * 6;                                    // [2][CCH][NN][NA]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_nu;
+    const int tid = threadIdx.x;
+    const int a = tid % GD_LANES, grp = tid / GD_LANES;
+    const int k0 = grp * KG;
+    const bool a_ok = a < NA;
+    const int aa = a_ok ? a : a - 4;  // dead lanes shadow a live lane of their own warp
+    const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
+    const float *F = feats + (size_t)z * c * p_in * NA;
+
+    for (int n = tid; n < NN; n += NTHR) s_raw[n] = n < nn ? idx[((size_t)z * p + pi) * nn + n] : -1;
+    __syncthreads();
+    if (tid < 32) {  // de-duplicate the repeat-filled row (see inter_group_tiles_kernel)
+        const int n = tid;
+        const int q = n < nn ? s_raw[n] : -1;
+        bool uniq = n < nn;
+        for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
+        int mult = 0;
+        for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, uniq);
+        const int pos = __popc(mask & ((1u << n) - 1u));
+        if (uniq) {
+            const float *X = g.xyz + (size_t)z * 3 * p_in;
+            const float *Cn = g.centers + (size_t)z * 3 * p;
+            s_idx[pos] = q;
+            s_mult[pos] = (float)mult;
+            s_g[pos * 3] = X[q] - Cn[pi];
+            s_g[pos * 3 + 1] = X[p_in + q] - Cn[p + pi];
+            s_g[pos * 3 + 2] = X[2 * p_in + q] - Cn[2 * p + pi];
+        }
+        const int cnt = __popc(mask);
+        if (n >= cnt && n < NN) {
+            s_idx[n] = 0; s_mult[n] = 0.f;
+            s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
+        }
+        if (n == 0) s_nu = cnt;
+    }
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    nn = s_nu;  // number of DISTINCT neighbours
+    for (int t = tid; t < 2 * CCH * (NN - nn) * NA; t += NTHR) {  // never-copied rows stay zero
+        const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
+        Fs[(bc * NN + n) * NA + e] = 0.f;
+    }
+
+    uint64_t w2[KG][NN / 2];
+    {
+        float R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
+#pragma unroll
+        for (int i = 0; i < KG; ++i) {
+            const float kx = __ldg(g.kernels + (k0 + i) * 3), ky = __ldg(g.kernels + (k0 + i) * 3 + 1),
+                        kz = __ldg(g.kernels + (k0 + i) * 3 + 2);
+            const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
+                        rz = R[6] * kx + R[7] * ky + R[8] * kz;
+#pragma unroll
+            for (int n = 0; n < NN; n += 2) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float t = kernel_weight_fast(s_g[(n + e) * 3], s_g[(n + e) * 3 + 1], s_g[(n + e) * 3 + 2], rx, ry, rz,
+                                                       1.0f / g.sigma);
+                    v[e] = (a_ok && n + e < nn) ? t * s_mult[n + e] : 0.f;
+                }
+                w2[i][n / 2] = pack_f32x2(v[0], v[1]);
+            }
+        }
+    }
+
+    const int nchunks = (c + CCH - 1) / CCH;
+    const uint32_t fs_u32 = smem_u32(Fs);
+    constexpr uint32_t ROW_BYTES = NA * 4;
+    auto issue = [&](int chunk, int buf) {
+        const int nch = min(CCH, c - chunk * CCH);
+        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(nch * nn) * ROW_BYTES);
+        for (int t = tid; t < nch * NN; t += NTHR) {
+            const int cl = t / NN, n = t % NN;
+            if (n < nn)
+                bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
+                         F + ((size_t)(chunk * CCH + cl) * p_in + s_idx[n]) * NA, ROW_BYTES, bar);
+        }
+    };
+
+    const long long row = (long long)z * cols_per_z + (long long)pl * NA + aa;  // this thread's tile row
+    uint8_t *row_base = tiles + ((size_t)(row >> 7) * k_blocks) * tile_bytes(TR_A) + (size_t)(row & 127) * 16;
+
+    uint32_t phase_bits = 0u;
+    issue(0, 0);
+    for (int chunk = 0; chunk < nchunks; ++chunk) {
+        const int buf = chunk & 1;
+        __syncthreads();  // every thread is done with the buffer the next gather overwrites
+        if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
+        mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
+        phase_bits ^= 1u << buf;
+        const float *fbase = Fs + (size_t)(buf * CCH * NN) * NA + aa;
+#pragma unroll 1
+        for (int blk = 0; blk < CCH / 4; ++blk) {
+            if ((chunk * CCH + blk * 4) >= c) break;  // c % 4 == 0: blocks of 4 channels are whole
+            uint32_t hi[12], lo[12];
+            const int kc0 = (chunk * (CCH / 4) + blk) * 12 + grp * 3;  // first of this thread's three K' chunks
+#pragma unroll
+            for (int cl4 = 0; cl4 < 4; ++cl4) {
+                uint64_t acc2[KG];
+#pragma unroll
+                for (int i = 0; i < KG; ++i) acc2[i] = 0ull;
+                const float *frow = fbase + (blk * 4 + cl4) * NN * NA;
+#pragma unroll
+                for (int n4 = 0; n4 < NN; n4 += 4) {
+                    if (n4 < nn) {  // CTA-uniform
+#pragma unroll
+                        for (int n = n4; n < n4 + 4; n += 2) {
+                            const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
+#pragma unroll
+                            for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(w2[i][n / 2], f2, acc2[i]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int ip = 0; ip < KG / 2; ++ip) {
+                    float e0, o0, e1, o1;
+                    unpack_f32x2(acc2[2 * ip], e0, o0);
+                    unpack_f32x2(acc2[2 * ip + 1], e1, o1);
+                    const float v0 = e0 + o0, v1 = e1 + o1;
+                    const __nv_bfloat162 hp = __floats2bfloat162_rn(v0, v1);
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
+                    const __nv_bfloat162 lp = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+                    hi[cl4 * 3 + ip] = hb;
+                    lo[cl4 * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                }
+                if (cl4 >= 1 && a_ok) {  // 6 (cl4 + 1) values so far: chunk j = cl4 - 1 (values 8j .. 8j+7) is complete
+                    const int j = cl4 - 1, kc = kc0 + j;
+                    uint8_t *dst = row_base + (size_t)(kc >> 2) * tile_bytes(TR_A) + (size_t)(kc & 3) * (TR_A * 16);
+                    *reinterpret_cast<uint4 *>(dst) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    *reinterpret_cast<uint4 *>(dst + part_bytes(TR_A)) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+        }
+    }
+}
+}  // namespace
+
+// Weight tiles of the forward GEMM (rows = c_out in trb-row tiles) with K in the permuted order K'(c,k).
+__global__ void __launch_bounds__(256)
+inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_out, int ck, int trb, int k_blocks) {
+    const int row = blockIdx.x * 32 + (threadIdx.x & 31), kcg = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int rows_pad = (c_out + trb - 1) / trb * trb;
+    if (row >= rows_pad || kcg >= k_blocks * (KB / 8)) return;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int kp = kcg * 8 + i;
+        x[i] = (row < c_out && kp < ck) ? __ldg(W + (size_t)row * ck + inter_kperm_inv(kp)) : 0.f;
+    }
+    uint4 hi, lo;
+    split8(x, hi, lo);
+    const int rt = row / trb, r = row - rt * trb;
+    uint8_t *tile = dst + ((size_t)rt * k_blocks + (kcg >> 2)) * tile_bytes(trb);
+    *reinterpret_cast<uint4 *>(tile + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = hi;
+    *reinterpret_cast<uint4 *>(tile + part_bytes(trb) + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = lo;
+}
+
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, cudaStream_t s) {
+    const int k_blocks = (ck + KB - 1) / KB, rows_pad = (c_out + trb - 1) / trb * trb;
+    dim3 grid((rows_pad + 31) / 32, (k_blocks * (KB / 8) + 7) / 8);
+    ProfScope prof(s, KC_SPLIT);
+    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks);
+    return check_launch("inter_w_tiles_kperm_kernel");
+}
+
+bool inter_group_direct_ok(const float *feats, int c, int nn, int na, int ks) {
+    return feats != nullptr && ks == GD_KS && na == GD_NA && nn <= GD_NN && c % 4 == 0;
+}
+
+// Returns 1 when the shape is not covered.  Tiles: rows = (z, pl, a) columns, K in the permuted order K'(c,k).
+int launch_inter_group_direct(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
+                              long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
+                              int ks, cudaStream_t s) {
+    if (!inter_group_direct_ok(feats, c, nn, na, ks) || bc > 65535) return 1;
+    const size_t smem = (size_t)(GD_NN * 6 + 2 * GD_CCH * GD_NN * GD_NA) * sizeof(float);
+    static bool set = false;
+    if (!set) {
+        cudaFuncSetAttribute(inter_group_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        set = true;
+    }
+    dim3 grid(p_cnt, bc);
+    ProfScope prof(s, KC_INTER_GROUP);
+    inter_group_direct_kernel<<<grid, GD_THR, smem, s>>>(feats, idx, g, static_cast<uint8_t *>(tiles), k_blocks, cols_per_z, c,
+                                                       p_in, p, nn, p_off);
+    return check_launch("inter_group_direct_kernel");
+}
+
+}  // namespace epn

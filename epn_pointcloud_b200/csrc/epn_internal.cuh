@@ -87,6 +87,18 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt,
                        int bc, int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
 
+// epn_group_direct.cu -- inter grouping (K <= 16) with the bf16 split in registers; the operand tiles use the
+// permuted K order  K'(c,k) = (c/4)*96 + (k/6)*24 + (c%4)*6 + (k%6)  (c % 4 == 0, 24 kernel points).
+__host__ __device__ __forceinline__ int inter_kperm_inv(int kp) {  // K' -> c*24 + k
+    const int blk = kp / 96, r = kp - blk * 96, grp = r / 24, q = r - grp * 24, cl4 = q / 6, i = q - cl4 * 6;
+    return (blk * 4 + cl4) * 24 + grp * 6 + i;
+}
+bool inter_group_direct_ok(const float *feats, int c, int nn, int na, int ks);
+int launch_inter_group_direct(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
+                              long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
+                              int ks, cudaStream_t s);
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, cudaStream_t s);
+
 // epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
                              int bc, int c, int p, int na, int kn, cudaStream_t s);
@@ -133,7 +145,7 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
 // (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles
 // (rows = c_out in trb-row tiles, K = n).
 int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, long long n, int trb, float *dW,
-                   cudaStream_t s);
+                   int kperm, cudaStream_t s);  // kperm: the tiles' K dimension is in the K'(c,k) order above
 
 // shapes the direct-to-tiles grouping kernels cover
 bool inter_group_tiles_ok(int nn, int na, int ks);
