@@ -45,9 +45,11 @@ static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused
 
 // Inter grouping with the bf16 split in registers + permuted K order (epn_group_direct.cu); EPN_DIRECT=0 keeps the
 // staging-tile kernel.  Forward and backward must agree, so the decision is a pure function of the call's shape.
-static bool inter_direct(const float *feats, int c_in, int nn, int na, int ks) {
-    static const int on = (getenv("EPN_DIRECT") && strcmp(getenv("EPN_DIRECT"), "0") == 0) ? 0 : 1;
-    return on && gemm_backend() == 0 && !fused_enabled() && inter_group_direct_ok(feats, c_in, nn, na, ks);
+static int inter_direct(const float *feats, int c_in, int nn, int na, int ks) {  // 0 or the K' mode
+    static const int on = getenv("EPN_DIRECT") ? atoi(getenv("EPN_DIRECT")) : 3;  // bit 0: K <= 16 kernel, bit 1: K <= 32 kernel
+    if (gemm_backend() != 0 || fused_enabled()) return 0;
+    const int mode = inter_group_direct_mode(feats, c_in, nn, na, ks);
+    return (mode && (on & (1 << (mode - 1)))) ? mode : 0;
 }
 
 static std::atomic<size_t> g_slab_bytes{0};
@@ -148,10 +150,10 @@ struct ColsView {
 constexpr long long HUGE_Z = 1LL << 60;
 
 static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s,
-                        bool kperm = false) {
+                        int kperm = 0) {
     if (gemm_backend() != 0) return 0;
     if (fwd && kperm) {
-        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), s);
+        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), kperm, s);
         if (rc) return rc;
     } else if (fwd) {
         SplitSrc src{W, HUGE_Z, 0, ck, HUGE_Z, 0, 1};
@@ -386,7 +388,7 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
-    const bool kperm = inter_direct(feats, c_in, nn, na, ks);
+    const int kperm = inter_direct(feats, c_in, nn, na, ks);
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm));
     if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && sp.pc == p && inter_fused_ok(c_in, c_out, p, nn, na, ks)) {
         // one launch over every cloud: G stays in shared memory; kept tiles (training) keep the slab layout the
@@ -482,7 +484,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             if (dW != nullptr && kept != nullptr) {
                 // dW += dout . G with G = the operand tiles the forward kept (K possibly in the permuted order)
-                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s, inter_direct(feats, c_in, nn, na, ks) ? 1 : 0));
+                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s, inter_direct(feats, c_in, nn, na, ks)));
             } else if (dW != nullptr) {
                 // dW += dout . G^T with G recomputed
                 const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int kk_t = blockIdx.x * TR_A + warp * 32 + lane;  // lanes <-> consecutive tile rows
-        const int kk = (p.kperm && kk_t < p.ck) ? inter_kperm_inv(kk_t) : kk_t;  // row of dW^T in the weight's own order
+        const int kk = (p.kperm && kk_t < p.ck) ? inter_kperm_inv(kk_t, p.kperm) : kk_t;  // row of dW^T in the weight's own order
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);

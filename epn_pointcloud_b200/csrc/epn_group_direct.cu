@@ -180,11 +180,194 @@ inter_group_direct_kernel(const float *__restrict__ feats, const int32_t *__rest
         }
     }
 }
+
+// ---- K <= 32 neighbours: 8 groups of 3 kernel points (512 threads, one CTA per SM), channels gathered 4 at a time.
+// A thread produces 3 values per channel, i.e. 24 values = three K chunks per EIGHT channels:
+//     K'(c, k) = (c/8)*192 + (k/3)*24 + (c%8)*3 + (k%3)
+constexpr int G3_NN = 32, G3_KG = 3, G3_CCH = 4;
+constexpr int G3_THR = GD_LANES * (GD_KS / G3_KG);  // 512
+
+__global__ void __launch_bounds__(G3_THR, 1)
+inter_group_direct32_kernel(const float *__restrict__ feats, const int32_t *__restrict__ idx, InterGeom g,
+                            uint8_t *__restrict__ tiles, int k_blocks, long long cols_per_z, int c, int p_in, int p, int nn,
+                            int p_off) {
+    constexpr int NN = G3_NN, KG = G3_KG, CCH = G3_CCH, NA = GD_NA, NTHR = G3_THR;
+    extern __shared__ __align__(16) float s_dyn[];
+    float *s_g = s_dyn;
+    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);
+    float *s_mult = s_dyn + NN * 4;
+    int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);
+    float *Fs = s_dyn + NN * 6;                                    // [2][CCH][NN][NA]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_nu;
+    const int tid = threadIdx.x;
+    const int a = tid % GD_LANES, grp = tid / GD_LANES;
+    const int k0 = grp * KG;
+    const bool a_ok = a < NA;
+    const int aa = a_ok ? a : a - 4;
+    const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
+    const float *F = feats + (size_t)z * c * p_in * NA;
+
+    for (int n = tid; n < NN; n += NTHR) s_raw[n] = n < nn ? idx[((size_t)z * p + pi) * nn + n] : -1;
+    __syncthreads();
+    if (tid < 32) {
+        const int n = tid;
+        const int q = n < nn ? s_raw[n] : -1;
+        bool uniq = n < nn;
+        for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
+        int mult = 0;
+        for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
+        const unsigned mask = __ballot_sync(0xffffffffu, uniq);
+        const int pos = __popc(mask & ((1u << n) - 1u));
+        if (uniq) {
+            const float *X = g.xyz + (size_t)z * 3 * p_in;
+            const float *Cn = g.centers + (size_t)z * 3 * p;
+            s_idx[pos] = q;
+            s_mult[pos] = (float)mult;
+            s_g[pos * 3] = X[q] - Cn[pi];
+            s_g[pos * 3 + 1] = X[p_in + q] - Cn[p + pi];
+            s_g[pos * 3 + 2] = X[2 * p_in + q] - Cn[2 * p + pi];
+        }
+        const int cnt = __popc(mask);
+        if (n >= cnt && n < NN) {
+            s_idx[n] = 0; s_mult[n] = 0.f;
+            s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
+        }
+        if (n == 0) s_nu = cnt;
+    }
+    const uint32_t bar0 = smem_u32(&s_bar[0]);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8u, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    nn = s_nu;
+    for (int t = tid; t < 2 * CCH * (NN - nn) * NA; t += NTHR) {
+        const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
+        Fs[(bc * NN + n) * NA + e] = 0.f;
+    }
+
+    uint64_t w2[KG][NN / 2];
+    {
+        float R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
+#pragma unroll
+        for (int i = 0; i < KG; ++i) {
+            const float kx = __ldg(g.kernels + (k0 + i) * 3), ky = __ldg(g.kernels + (k0 + i) * 3 + 1),
+                        kz = __ldg(g.kernels + (k0 + i) * 3 + 2);
+            const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
+                        rz = R[6] * kx + R[7] * ky + R[8] * kz;
+#pragma unroll
+            for (int n = 0; n < NN; n += 2) {
+                float v[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const float t = kernel_weight_fast(s_g[(n + e) * 3], s_g[(n + e) * 3 + 1], s_g[(n + e) * 3 + 2], rx, ry, rz,
+                                                       1.0f / g.sigma);
+                    v[e] = (a_ok && n + e < nn) ? t * s_mult[n + e] : 0.f;
+                }
+                w2[i][n / 2] = pack_f32x2(v[0], v[1]);
+            }
+        }
+    }
+
+    const int nchunks = c / CCH;  // c % 8 == 0: an even number of whole chunks
+    const uint32_t fs_u32 = smem_u32(Fs);
+    constexpr uint32_t ROW_BYTES = NA * 4;
+    auto issue = [&](int chunk, int buf) {
+        const uint32_t bar = bar0 + 8u * (uint32_t)buf;
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
+        for (int t = tid; t < CCH * NN; t += NTHR) {
+            const int cl = t / NN, n = t % NN;
+            if (n < nn)
+                bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
+                         F + ((size_t)(chunk * CCH + cl) * p_in + s_idx[n]) * NA, ROW_BYTES, bar);
+        }
+    };
+
+    const long long row = (long long)z * cols_per_z + (long long)pl * NA + aa;
+    uint8_t *row_base = tiles + ((size_t)(row >> 7) * k_blocks) * tile_bytes(TR_A) + (size_t)(row & 127) * 16;
+    auto store_chunk = [&](int kc, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t l0, uint32_t l1, uint32_t l2,
+                           uint32_t l3) {
+        uint8_t *dst = row_base + (size_t)(kc >> 2) * tile_bytes(TR_A) + (size_t)(kc & 3) * (TR_A * 16);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(h0, h1, h2, h3);
+        *reinterpret_cast<uint4 *>(dst + part_bytes(TR_A)) = make_uint4(l0, l1, l2, l3);
+    };
+
+    uint32_t phase_bits = 0u;
+    issue(0, 0);
+#pragma unroll 1
+    for (int blk = 0; blk < nchunks / 2; ++blk) {
+        uint32_t hi[12], lo[12];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int chunk = blk * 2 + half, buf = half;  // chunk parity == half
+            __syncthreads();  // every thread is done with the buffer the next gather overwrites
+            if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
+            mbar_wait(bar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
+            phase_bits ^= 1u << buf;
+            const float *fbase = Fs + (size_t)(buf * CCH * NN) * NA + aa;
+#pragma unroll
+            for (int cp = 0; cp < CCH / 2; ++cp) {  // two channels -> 6 values -> 3 packed pairs
+                uint64_t acc2[2][KG];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < KG; ++i) acc2[h][i] = 0ull;
+#pragma unroll
+                for (int n4 = 0; n4 < NN; n4 += 4) {
+                    if (n4 < nn) {  // CTA-uniform
+#pragma unroll
+                        for (int n = n4; n < n4 + 4; n += 2) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const float *frow = fbase + (cp * 2 + h) * NN * NA;
+                                const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
+#pragma unroll
+                                for (int i = 0; i < KG; ++i) acc2[h][i] = fma_f32x2(w2[i][n / 2], f2, acc2[h][i]);
+                            }
+                        }
+                    }
+                }
+                float v[6];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int i = 0; i < KG; ++i) {
+                        float e, o;
+                        unpack_f32x2(acc2[h][i], e, o);
+                        v[h * KG + i] = e + o;
+                    }
+#pragma unroll
+                for (int ip = 0; ip < 3; ++ip) {
+                    const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * ip], v[2 * ip + 1]);
+                    const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
+                    const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * ip] - __uint_as_float(hb << 16),
+                                                                    v[2 * ip + 1] - __uint_as_float(hb & 0xffff0000u));
+                    hi[half * 6 + cp * 3 + ip] = hb;
+                    lo[half * 6 + cp * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                }
+            }
+            const int kc0 = blk * 24 + grp * 3;  // first of this thread's three K' chunks of the 8-channel block
+            if (a_ok) {
+                if (half == 0) {
+                    store_chunk(kc0, hi[0], hi[1], hi[2], hi[3], lo[0], lo[1], lo[2], lo[3]);
+                } else {
+                    store_chunk(kc0 + 1, hi[4], hi[5], hi[6], hi[7], lo[4], lo[5], lo[6], lo[7]);
+                    store_chunk(kc0 + 2, hi[8], hi[9], hi[10], hi[11], lo[8], lo[9], lo[10], lo[11]);
+                }
+            }
+        }
+    }
+}
 }  // namespace
 
 // Weight tiles of the forward GEMM (rows = c_out in trb-row tiles) with K in the permuted order K'(c,k).
 __global__ void __launch_bounds__(256)
-inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_out, int ck, int trb, int k_blocks) {
+inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_out, int ck, int trb, int k_blocks,
+                           int mode) {
     const int row = blockIdx.x * 32 + (threadIdx.x & 31), kcg = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int rows_pad = (c_out + trb - 1) / trb * trb;
     if (row >= rows_pad || kcg >= k_blocks * (KB / 8)) return;
@@ -192,7 +375,7 @@ inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ ds
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int kp = kcg * 8 + i;
-        x[i] = (row < c_out && kp < ck) ? __ldg(W + (size_t)row * ck + inter_kperm_inv(kp)) : 0.f;
+        x[i] = (row < c_out && kp < ck) ? __ldg(W + (size_t)row * ck + inter_kperm_inv(kp, mode)) : 0.f;
     }
     uint4 hi, lo;
     split8(x, hi, lo);
@@ -202,33 +385,44 @@ inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ ds
     *reinterpret_cast<uint4 *>(tile + part_bytes(trb) + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = lo;
 }
 
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, cudaStream_t s) {
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, cudaStream_t s) {
     const int k_blocks = (ck + KB - 1) / KB, rows_pad = (c_out + trb - 1) / trb * trb;
     dim3 grid((rows_pad + 31) / 32, (k_blocks * (KB / 8) + 7) / 8);
     ProfScope prof(s, KC_SPLIT);
-    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks);
+    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks, mode);
     return check_launch("inter_w_tiles_kperm_kernel");
 }
 
-bool inter_group_direct_ok(const float *feats, int c, int nn, int na, int ks) {
-    return feats != nullptr && ks == GD_KS && na == GD_NA && nn <= GD_NN && c % 4 == 0;
+// 0: not covered; 1: K <= 16 kernel (K' over 4-channel blocks); 2: K <= 32 kernel (K' over 8-channel blocks)
+int inter_group_direct_mode(const float *feats, int c, int nn, int na, int ks) {
+    if (feats == nullptr || ks != GD_KS || na != GD_NA) return 0;
+    if (nn <= GD_NN && c % 4 == 0) return 1;
+    if (nn <= G3_NN && c % 8 == 0) return 2;
+    return 0;
 }
 
 // Returns 1 when the shape is not covered.  Tiles: rows = (z, pl, a) columns, K in the permuted order K'(c,k).
 int launch_inter_group_direct(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
                               long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
                               int ks, cudaStream_t s) {
-    if (!inter_group_direct_ok(feats, c, nn, na, ks) || bc > 65535) return 1;
-    const size_t smem = (size_t)(GD_NN * 6 + 2 * GD_CCH * GD_NN * GD_NA) * sizeof(float);
+    const int mode = inter_group_direct_mode(feats, c, nn, na, ks);
+    if (mode == 0 || bc > 65535) return 1;
     static bool set = false;
+    const size_t smem1 = (size_t)(GD_NN * 6 + 2 * GD_CCH * GD_NN * GD_NA) * sizeof(float);
+    const size_t smem2 = (size_t)(G3_NN * 6 + 2 * G3_CCH * G3_NN * GD_NA) * sizeof(float);
     if (!set) {
-        cudaFuncSetAttribute(inter_group_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(inter_group_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+        cudaFuncSetAttribute(inter_group_direct32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
         set = true;
     }
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_GROUP);
-    inter_group_direct_kernel<<<grid, GD_THR, smem, s>>>(feats, idx, g, static_cast<uint8_t *>(tiles), k_blocks, cols_per_z, c,
-                                                       p_in, p, nn, p_off);
+    if (mode == 1)
+        inter_group_direct_kernel<<<grid, GD_THR, smem1, s>>>(feats, idx, g, static_cast<uint8_t *>(tiles), k_blocks, cols_per_z,
+                                                           c, p_in, p, nn, p_off);
+    else
+        inter_group_direct32_kernel<<<grid, G3_THR, smem2, s>>>(feats, idx, g, static_cast<uint8_t *>(tiles), k_blocks,
+                                                             cols_per_z, c, p_in, p, nn, p_off);
     return check_launch("inter_group_direct_kernel");
 }
 

@@ -87,17 +87,22 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt,
                        int bc, int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
 
-// epn_group_direct.cu -- inter grouping (K <= 16) with the bf16 split in registers; the operand tiles use the
-// permuted K order  K'(c,k) = (c/4)*96 + (k/6)*24 + (c%4)*6 + (k%6)  (c % 4 == 0, 24 kernel points).
-__host__ __device__ __forceinline__ int inter_kperm_inv(int kp) {  // K' -> c*24 + k
-    const int blk = kp / 96, r = kp - blk * 96, grp = r / 24, q = r - grp * 24, cl4 = q / 6, i = q - cl4 * 6;
-    return (blk * 4 + cl4) * 24 + grp * 6 + i;
+// epn_group_direct.cu -- inter grouping with the bf16 split in registers; the operand tiles use a permuted K order
+// (24 kernel points):  mode 1 (K <= 16 neighbours, c % 4 == 0)  K'(c,k) = (c/4)*96  + (k/6)*24 + (c%4)*6 + (k%6)
+//                      mode 2 (K <= 32 neighbours, c % 8 == 0)  K'(c,k) = (c/8)*192 + (k/3)*24 + (c%8)*3 + (k%3)
+__host__ __device__ __forceinline__ int inter_kperm_inv(int kp, int mode) {  // K' -> c*24 + k
+    if (mode == 1) {
+        const int blk = kp / 96, r = kp - blk * 96, grp = r / 24, q = r - grp * 24, cl4 = q / 6, i = q - cl4 * 6;
+        return (blk * 4 + cl4) * 24 + grp * 6 + i;
+    }
+    const int blk = kp / 192, r = kp - blk * 192, grp = r / 24, q = r - grp * 24, c8 = q / 3, i = q - c8 * 3;
+    return (blk * 8 + c8) * 24 + grp * 3 + i;
 }
-bool inter_group_direct_ok(const float *feats, int c, int nn, int na, int ks);
+int inter_group_direct_mode(const float *feats, int c, int nn, int na, int ks);  // 0 = shape not covered
 int launch_inter_group_direct(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
                               long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
                               int ks, cudaStream_t s);
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, cudaStream_t s);
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, cudaStream_t s);
 
 // epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
@@ -145,7 +150,7 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
 // (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles
 // (rows = c_out in trb-row tiles, K = n).
 int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, long long n, int trb, float *dW,
-                   int kperm, cudaStream_t s);  // kperm: the tiles' K dimension is in the K'(c,k) order above
+                   int kperm, cudaStream_t s);  // kperm: mode of the K'(c,k) order of the tiles (0 = plain)
 
 // shapes the direct-to-tiles grouping kernels cover
 bool inter_group_tiles_ok(int nn, int na, int ks);

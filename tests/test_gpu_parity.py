@@ -445,7 +445,7 @@ def test_umma_engine_matches_simt_inter(E, both_backends, c_in, c_out, p_in, str
 ])
 def test_fused_inter_conv_matches_two_kernel_schedule(E, c_in, c_out, p_in, stride, nn_, b):
     """The fused kernel (gather + contraction + GEMM from shared memory) against the grouping-kernel + GEMM-kernel
-    schedule of the same engine: same operand rounding, so the outputs agree to fp32 summation order; the kept
+    schedule of the same engine: same operand rounding, so the outputs agree up to the fp32 summation order; the kept
     operand tiles it writes for the weight gradient must give the same dW; inference (no kept tiles) too."""
     conv = _layer(E, c_in, c_out, stride, nn_, 0.45, 0.1)
     xyz = sphere(b, p_in, 23).to(DEV)
@@ -466,7 +466,9 @@ def test_fused_inter_conv_matches_two_kernel_schedule(E, c_in, c_out, p_in, stri
     finally:
         E.ops.set_fused_inter(bool(default))
     for a, b_, name in zip(res[True], res[False], ("out", "dfeats", "dW", "out_no_grad")):
-        assert rel_err(a, b_) < 2e-6, name
+        # same bf16 hi/lo operands; the two schedules order the K dimension differently (the grouping kernels
+        # permute it), so the fp32 accumulation order differs: the bar both hold against the fp32 SIMT engine
+        assert rel_err(a, b_) < 3e-5, name
 
 
 @pytest.mark.parametrize("c_in,c_out,p", [(4, 8, 32), (64, 64, 512), (128, 128, 256), (256, 256, 128), (5, 300, 17)])
