@@ -127,7 +127,7 @@ int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void 
 }
 
 // ------------------------------------------------------------------ inter scatter
-constexpr int SC_LANES = 64, SC_KS = 24, SC_NB = 4, SC_CCH = 4;
+constexpr int SC_LANES = 64, SC_KS = 24, SC_NB = 4, SC_CCH = 4, SC_BUFS = 3;
 
 template <int NN, int NA>
 __global__ void __launch_bounds__(SC_LANES *(NN / SC_NB), NN == 16 ? 2 : 1)
@@ -139,7 +139,7 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
     int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]     distinct neighbour indices
     float *s_mult = s_dyn + NN * 4;                                // [NN]     multiplicities
     int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     ball-query row as stored
-    float *Ds = s_dyn + NN * 6;                                    // [2][SC_CCH*24][NA]
+    float *Ds = s_dyn + NN * 6;                                    // [SC_BUFS][SC_CCH*24][NA]
     __shared__ int s_nu;
     const int tid = threadIdx.x;
     const int a = tid % SC_LANES, grp = tid / SC_LANES;
@@ -225,16 +225,19 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
+    // three staging buffers, ONE barrier per chunk: the barrier that publishes chunk i also proves that every thread
+    // has finished chunk i-1, whose buffer the copies of chunk i+2 (issued right after it) overwrite
     issue(0, 0);
+    if (nchunks > 1) issue(1, 1);
     for (int chunk = 0; chunk < nchunks; ++chunk) {
-        const int buf = chunk & 1;
+        const int buf = chunk % SC_BUFS;
         if (chunk + 1 < nchunks) {
-            issue(chunk + 1, buf ^ 1);
             asm volatile("cp.async.wait_group 1;" ::: "memory");
         } else {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        __syncthreads();  // rows of this chunk visible to every thread
+        __syncthreads();  // rows of this chunk visible to every thread; everybody is done with chunk - 1
+        if (chunk + 2 < nchunks) issue(chunk + 2, (chunk + 2) % SC_BUFS);
         const float *dbase = Ds + (size_t)(buf * SC_CCH * SC_KS) * NA + aa;
 #pragma unroll 2
         for (int cl = 0; cl < SC_CCH; ++cl) {
@@ -259,7 +262,6 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
             for (int j = 0; j < SC_NB; ++j)
                 if (a_ok && n0 + j < nn) atomicAdd(dplane + qoff[j], t[j]);
         }
-        __syncthreads();  // all reads of Ds[buf] done before the copies of chunk+2 overwrite it
     }
 }
 
@@ -274,16 +276,16 @@ int launch_inter_scatter(const float *dG, long long stride_b, long long stride_c
     ProfScope prof(s, KC_INTER_SCATTER);
     static bool set = false;
     if (!set) {
-        cudaFuncSetAttribute(inter_scatter_kernel<16, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(inter_scatter_kernel<32, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(inter_scatter_kernel<16, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        cudaFuncSetAttribute(inter_scatter_kernel<32, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         set = true;
     }
     if (nn <= 16) {
-        const size_t smem = (size_t)(16 * 6 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(16 * 6 + SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<16, 60><<<grid, SC_LANES * (16 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     } else {
-        const size_t smem = (size_t)(32 * 6 + 2 * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(32 * 6 + SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<32, 60><<<grid, SC_LANES * (32 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     }
