@@ -14,7 +14,7 @@ import re
 import sys
 
 CLASS_OF = [("umma_gemm", "channel_gemm"), ("umma_dw", "channel_gemm"), ("inter_fused", "inter_fused_fwd"),
-            ("intra_wt_tiles", "split_convert"), ("sgemm", "channel_gemm"), ("inter_group_tiles", "inter_group_fwd"),
+            ("intra_wt_tiles", "split_convert"), ("sgemm", "channel_gemm"), ("inter_group_tiles", "inter_group_fwd"), ("inter_group_direct", "inter_group_fwd"), ("inter_w_tiles", "split_convert"),
             ("inter_group_fwd", "inter_group_fwd"), ("inter_scatter", "inter_group_bwd_scatter"),
             ("inter_group_bwd", "inter_group_bwd_scatter"), ("intra_", "intra_group"), ("split_tiles", "split_convert"),
             ("norm_", "norm_act"), ("ball_query", "index_ops"), ("fps_kernel", "index_ops"), ("gather_", "index_ops")]
