@@ -66,8 +66,14 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 4) {
-        // producer: every lane owns one (forward k-block, part, 8-kk group) piece of the A stage
+    if (warp != 5) {
+        // producers: every lane owns one (forward k-block, part, 8-kk group) piece of the A stage.  A warp can issue
+        // these 1-KB bulk copies only at ~26 GB/s (measured: one issuing warp per SM streams 3.8 TB/s, two 6.5 TB/s,
+        // while 16-KB copies reach 7.5 TB/s from a single warp), so one warp PER PIPELINE STAGE issues them: warp w
+        // owns ring slot w (iterations w, w + stages, ...), which also keeps every waiter at most one phase behind its
+        // barrier (a warp roaming over slots could run two phases ahead and alias the parity).  Warps 0-3 turn into
+        // the epilogue afterwards.
+        const int NPW = p.stages;  // <= 4
         const int j = lane >> 3, part = (lane >> 2) & 1, kc = lane & 3;
         const int kb = 4 * blockIdx.x + j;
         const bool has = kb < p.g_k_blocks;
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
         const uint32_t a_dst = (uint32_t)part * A_PART + (uint32_t)(j * 4 + kc) * (UNIT * 16);
         const size_t a_off = (size_t)kb * tile_bytes(TR_A) + (size_t)part * part_bytes(TR_A) + (size_t)kc * (TR_A * 16);
         const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.b_k_blocks) * b_tile;
-        for (int i = 0; i < nu; ++i) {
+        for (int i = warp; i < nu && warp < NPW; i += NPW) {
             const int s = i % p.stages;
             const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
             const int u = u0 + i;
@@ -90,7 +96,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
             if (lane < 2)
                 bulk_g2s(st + A_STAGE + lane * b_tile, b_src + (size_t)(2 * u + lane) * b_tile, b_tile, full_bar(s));
         }
-    } else if (warp == 5) {
+    } else {
         if (lane == 0) {
             const uint32_t idesc = instr_desc_bf16_m128(p.trb) | (1u << 15);  // A is MN-major
             const uint32_t b_lbo = (uint32_t)p.trb * 16;
@@ -117,7 +123,8 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
             }
             mma_commit(accum_bar);
         }
-    } else {
+    }
+    if (warp < 4) {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const int kk_t = blockIdx.x * TR_A + warp * 32 + lane;  // lanes <-> consecutive tile rows
