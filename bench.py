@@ -67,13 +67,13 @@ def algorithmic_work(batch):
         has_dx = c_in > 1  # layer 0: feats == 1, no dfeats
         gemm_f += inter_gemm * (2 + (1 if has_dx else 0)) + intra_gemm * 3          # fwd + dW (+ dX)
         spatial = 2.0 * c_in * p * A * KS * k + 11.0 * p * A * KS * k
-        group_f += 2 * spatial                                                      # fwd + recompute for dW
+        group_f += spatial                                                          # forward only: dW reads the kept tiles
         scatter_f += spatial if has_dx else 0.0
         grouped = 4.0 * c_in * KS * p * A
         feats_in = 4.0 * c_in * p_in * A if has_dx else 0.0
-        group_b += 2 * (feats_in + 12.0 * p_in + 4.0 * p * k + grouped)
+        group_b += feats_in + 12.0 * p_in + 4.0 * p * k + grouped
         scatter_b += (feats_in + 12.0 * p_in + 4.0 * p * k + grouped) if has_dx else 0.0
-        intra_b += 3 * (4.0 * c_out * p * A + 4.0 * c_out * KN * p * A)
+        intra_b += 4.0 * c_out * p * A + 4.0 * c_out * KN * p * A                   # training forward gather into kept tiles
     return {"channel_gemm": (gemm_f * batch, None), "inter_group_fwd": (group_f * batch, group_b * batch),
             "inter_group_bwd_scatter": (scatter_f * batch, scatter_b * batch), "intra_group": (None, intra_b * batch)}
 
