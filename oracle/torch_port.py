@@ -214,3 +214,55 @@ def layers_from_module(backbone):
             layers.append((prm, param["args"], intra_idx, sd["inter_conv.conv.anchors"],
                            sd["inter_conv.conv.kernels"]))
     return layers
+
+
+# ------------------------------------------------------- heads of the other two shipped models (8 f2)
+def _pointnet_so3(xyz, feats, w, b, anchors):
+    """PointnetSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:218-235): centred coordinates rotated into every anchor
+    frame, concatenated to the features, 1x1 conv, max over points -> [nb, c_out, na]."""
+    c = xyz - xyz.mean(2, keepdim=True)
+    na = feats.shape[3]
+    if na == 1:
+        x = torch.cat([feats, c[..., None]], 1)
+    else:
+        x = torch.cat([feats, torch.einsum("aji,bjn->bina", anchors.to(feats.dtype), c.to(feats.dtype))], 1)
+    return F.conv2d(x, w, b).max(2)[0]
+
+
+def inv_head(xyz, feats, hp):
+    """InvOutBlockMVD.forward (SPConvNets/utils/base_so3conv.py:596-613).  hp: {att0_w, att0_b, att2_w, att2_b,
+    pn_w, pn_b, anchors} -> (descriptor [nb, c_out] L2-normalised, attention [nb, c, np, na])."""
+    nb = feats.shape[0]
+    attn = F.conv2d(F.relu(F.conv2d(feats, hp["att0_w"], hp["att0_b"])), hp["att2_w"], hp["att2_b"])
+    attn = F.softmax(attn, dim=3)
+    x = (feats * attn).sum(-1, keepdim=True)
+    x = _pointnet_so3(xyz, x, hp["pn_w"], hp["pn_b"], hp["anchors"]).view(nb, -1)
+    return F.normalize(x, p=2, dim=1), attn
+
+
+def rel_head(f1, f2, x1, x2, hp):
+    """RelSO3OutBlockR.forward (SPConvNets/utils/base_so3conv.py:696-730).  hp: {pn_w, pn_b, anchors, lin_w[], lin_b[],
+    att_w, att_b, reg_w, reg_b, temperature} -> (confidence [nb, na, na], y [nb, n_out, na, na])."""
+    p1 = F.relu(_pointnet_so3(x1, f1, hp["pn_w"], hp["pn_b"], hp["anchors"]))
+    p2 = F.relu(_pointnet_so3(x2, f2, hp["pn_w"], hp["pn_b"], hp["anchors"]))
+    nb, na = p1.shape[0], p1.shape[2]
+    x = torch.cat((p1.unsqueeze(-2).expand(-1, -1, na, -1), p2.unsqueeze(-1).expand(-1, -1, -1, na)), 1).contiguous()
+    for w, b in zip(hp["lin_w"], hp["lin_b"]):
+        x = F.relu(F.conv2d(x, w, b))
+    conf = F.softmax(F.conv2d(x, hp["att_w"], hp["att_b"]).view(nb, na, na) * hp["temperature"], dim=1)
+    return conf, F.conv2d(x, hp["reg_w"], hp["reg_b"])
+
+
+def inv_head_from_state(sd):
+    """state_dict of an InvOutBlockMVD (reference or mirror; keys relative to the block)."""
+    return {"att0_w": sd["attention_layer.0.weight"], "att0_b": sd["attention_layer.0.bias"],
+            "att2_w": sd["attention_layer.2.weight"], "att2_b": sd["attention_layer.2.bias"],
+            "pn_w": sd["pointnet.embed.weight"], "pn_b": sd["pointnet.embed.bias"], "anchors": sd["pointnet.anchors"]}
+
+
+def rel_head_from_state(sd, temperature):
+    n = len([k for k in sd if k.startswith("linear.") and k.endswith(".weight")])
+    return {"pn_w": sd["pointnet.embed.weight"], "pn_b": sd["pointnet.embed.bias"], "anchors": sd["pointnet.anchors"],
+            "lin_w": [sd["linear.%d.weight" % i] for i in range(n)], "lin_b": [sd["linear.%d.bias" % i] for i in range(n)],
+            "att_w": sd["attention_layer.weight"], "att_b": sd["attention_layer.bias"],
+            "reg_w": sd["regressor_layer.weight"], "reg_b": sd["regressor_layer.bias"], "temperature": temperature}

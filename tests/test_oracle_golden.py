@@ -215,3 +215,42 @@ def test_inv_and_reg_model_arithmetic_and_state_dicts_match_reference():
         ref = g[name + "_state_shapes_all"]
         assert {k: v for k, v in shapes.items() if not k.endswith("_intra_idx32")} == ref
         assert sum(p.numel() for p in model.parameters()) == g[name + "_n_params"]
+
+
+def _strip(sd, prefix):
+    return {k[len(prefix):]: v.float() for k, v in sd.items() if k.startswith(prefix)}
+
+
+def test_port_matches_reference_inv_model():
+    """oracle/torch_port.py (backbone + InvOutBlockMVD restatement) against the reference's own 3DMatch model output
+    (tests/golden/inv_model_small.npz, made by oracle/make_golden_models.py): pins the CPU oracle for row 8 f2."""
+    import torch
+    from conftest import load_golden, rel_err
+    from epn_pointcloud_b200.heads import InvSO3ConvModel
+    from oracle import torch_port as TP
+    g = load_golden("inv_model_small")
+    model = InvSO3ConvModel(g["params"])
+    model.load_state_dict(g.state_dict(), strict=True)
+    with torch.no_grad():
+        xyz, feats = TP.backbone_forward(g["pc"], TP.layers_from_module(model))
+        desc, attn = TP.inv_head(xyz, feats, TP.inv_head_from_state(_strip(model.state_dict(), "outblock.")))
+    assert rel_err(desc, g["desc"]) < 1e-5 and rel_err(attn, g["attn"]) < 1e-5
+
+
+def test_port_matches_reference_reg_model():
+    """Same for the relative-rotation model (shared backbone over both clouds of a pair + RelSO3OutBlockR)."""
+    import torch
+    from conftest import load_golden, rel_err
+    from epn_pointcloud_b200.heads import RegSO3ConvModel
+    from oracle import torch_port as TP
+    g = load_golden("reg_model_small")
+    model = RegSO3ConvModel(g["params"])
+    model.load_state_dict(g.state_dict(), strict=True)
+    x = torch.cat((g["pairs"][:, 0], g["pairs"][:, 1]), dim=0)
+    with torch.no_grad():
+        xyz, feats = TP.backbone_forward(x, TP.layers_from_module(model))
+        f1, f2 = torch.chunk(feats, 2, dim=0)
+        x1, x2 = torch.chunk(xyz, 2, dim=0)
+        hp = TP.rel_head_from_state(_strip(model.state_dict(), "outblock."), g["params"]["outblock"]["temperature"])
+        conf, quats = TP.rel_head(f1, f2, x1, x2, hp)
+    assert rel_err(conf, g["conf"]) < 1e-5 and rel_err(quats, g["quats"]) < 1e-5
