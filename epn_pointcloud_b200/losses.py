@@ -1,0 +1,230 @@
+"""Training losses and rotation utilities of the three shipped tasks.
+
+Host-side PyTorch only (tiny tensors; nothing here is on the hot path), device agnostic.  Mirrors with the
+reference's names, constructor arguments and return tuples:
+  vgtk/vgtk/loss.py:18-75      CrossEntropyLoss, AttentionCrossEntropyLoss        (ModelNet40 classification)
+  vgtk/vgtk/loss.py:77-218     MultiTaskDetectionLoss, angle_from_R, mean_angular_error   (relative rotation)
+  vgtk/vgtk/loss.py:220-318    pairwise_distance_matrix, batch_hard_negative_mining, TripletBatchLoss (3DMatch;
+                               the invariance term; the optional equivariance term, alpha > 0, is not mirrored)
+  vgtk/vgtk/functional/rotation.py:379-519   quaternion / 6-D -> rotation matrix, chordal SO(3) mean
+  vgtk/vgtk/spconv/functional.py:138-143     acos_safe
+Unlike the reference's rotation helpers these do not hard-code `.cuda()` (rotation.py:385,449), so they also run in
+the CPU tests that pin them against reference outputs (tests/golden/losses.npz, oracle/make_golden_losses.py).
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# ------------------------------------------------------------------ rotation utilities
+def acos_safe(x, eps=1e-4):
+    """acos with the ends replaced by their tangent lines so the gradient stays finite at |x| -> 1."""
+    slope = math.acos(1.0 - eps) / eps
+    s = torch.sign(x)
+    inner = torch.acos(x.clamp(-1.0 + eps, 1.0 - eps))
+    outer = torch.acos(s * (1.0 - eps)) - slope * s * (x.abs() - 1.0 + eps)
+    return torch.where(x.abs() <= 1.0 - eps, inner, outer)
+
+
+def _unit(v):
+    return v / v.norm(dim=1, keepdim=True).clamp_min(1e-8)
+
+
+def compute_rotation_matrix_from_quaternion(quaternion):
+    """[n, 4] (w, x, y, z), any norm -> [n, 3, 3]."""
+    q = _unit(quaternion)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    rows = [1 - 2 * y * y - 2 * z * z, 2 * x * y - 2 * z * w, 2 * x * z + 2 * y * w,
+            2 * x * y + 2 * z * w, 1 - 2 * x * x - 2 * z * z, 2 * y * z - 2 * x * w,
+            2 * x * z - 2 * y * w, 2 * y * z + 2 * x * w, 1 - 2 * x * x - 2 * y * y]
+    return torch.stack(rows, dim=1).view(-1, 3, 3)
+
+
+def compute_rotation_matrix_from_ortho6d(ortho6d):
+    """[n, 6] = two 3-vectors -> [n, 3, 3] by Gram-Schmidt (columns x, y, z)."""
+    x = _unit(ortho6d[:, 0:3])
+    z = _unit(torch.cross(x, ortho6d[:, 3:6], dim=1))
+    y = torch.cross(z, x, dim=1)
+    return torch.stack((x, y, z), dim=2)
+
+
+def so3_mean(Rs, weights=None):
+    """Chordal L2 mean of rotations: Rs [b, n, 3, 3], weights [b, n] or None -> [b, 3, 3] (projection of the weighted
+    sum onto SO(3) through its SVD, determinant fixed to +1)."""
+    m = Rs.sum(dim=1) if weights is None else (weights[:, :, None, None] * Rs).sum(dim=1)
+    u, _, v = torch.svd(m)
+    vt = v.transpose(1, 2)
+    d = torch.ones(m.shape[0], 3, dtype=m.dtype, device=m.device)
+    d[:, 2] = torch.det(torch.matmul(u, vt))
+    return torch.matmul(u * d[:, None, :], vt)
+
+
+def angle_from_R(R):
+    return acos_safe(0.5 * (R.diagonal(dim1=-2, dim2=-1).sum(-1) - 1.0))
+
+
+def mean_angular_error(pred_R, gt_R):
+    """Per-sample geodesic angle between prediction and ground truth (the reference does not average either)."""
+    return angle_from_R(torch.matmul(pred_R, gt_R.transpose(1, 2).float()))
+
+
+# ------------------------------------------------------------------ classification
+class CrossEntropyLoss(nn.Module):
+    """-> (cross entropy, accuracy)."""
+
+    def __init__(self):
+        super().__init__()
+        self.metric = nn.CrossEntropyLoss()
+
+    def forward(self, pred, label):
+        hit = pred.max(1)[1].reshape(-1) == label.reshape(-1)
+        return self.metric(pred, label), hit.sum().float() / float(hit.numel())
+
+
+class AttentionCrossEntropyLoss(nn.Module):
+    """Class loss + (optionally scheduled) rotation-anchor classification loss on the attention weights."""
+
+    def __init__(self, loss_type, loss_margin):
+        super().__init__()
+        self.metric = CrossEntropyLoss()
+        self.loss_type = loss_type
+        self.loss_margin = loss_margin
+        self.iter_counter = 0
+
+    def forward(self, pred, label, wts, rlabel, pretrain_step=2000):
+        cls_loss, acc = self.metric(pred, label)
+        if wts.ndimension() == 3:      # [b, c, a] weights: one anchor label per channel, then classes on dim 1
+            c = wts.shape[1]
+            rlabel = rlabel[:, :c] if c <= rlabel.shape[1] else rlabel.repeat(1, 10)[:, :c]
+            wts = wts.transpose(1, 2)
+        r_loss, racc = self.metric(wts, rlabel)
+        m = self.loss_margin
+        if self.loss_type == "schedule":
+            t = min(float(self.iter_counter) / pretrain_step, 1.0)
+            loss = t * cls_loss + (m + 1.0 - t) * r_loss
+        elif self.loss_type == "default":
+            loss = cls_loss + m * r_loss
+        elif self.loss_type == "no_reg":
+            loss = cls_loss
+        else:
+            raise NotImplementedError("%s is not Implemented!" % self.loss_type)
+        if self.training:
+            self.iter_counter += 1
+        return loss, cls_loss, r_loss, acc, racc
+
+
+# ------------------------------------------------------------------ relative rotation
+def batched_select_anchor(labels, y, rotation_mapping):
+    """y [b, c, na_tgt, na_src], labels [b, na_src] (chosen target anchor per source anchor) -> the c-vector at
+    (labels[b, s], s) mapped to a rotation: [b, na_src, 3, 3]."""
+    b, na = labels.shape
+    idx = labels.long().view(b, 1, 1, na).expand(b, y.shape[1], 1, na)
+    picked = torch.gather(y, 2, idx).squeeze(2).transpose(1, 2).reshape(b * na, -1)
+    return rotation_mapping(picked).view(b, na, 3, 3)
+
+
+class MultiTaskDetectionLoss(nn.Module):
+    """Anchor classification + rotation-residual regression; three settings as in the reference
+    (single anchor / anchor alignment of a pair / canonical regression of one shape)."""
+
+    def __init__(self, anchors, nr=4, w=10, threshold=1.0):
+        super().__init__()
+        assert nr == 4 or nr == 6
+        self.classifier = CrossEntropyLoss()
+        self.anchors = anchors
+        self.nr = nr
+        self.w = w
+        self.threshold = threshold
+        self.iter_counter = 0
+
+    def forward(self, wts, label, y, gt_R, gt_T=None):
+        b, nr, na = wts.shape[0], self.nr, wts.shape[1]
+        to_R = compute_rotation_matrix_from_quaternion if nr == 4 else compute_rotation_matrix_from_ortho6d
+        true_R = gt_R[:, 29] if gt_T is None else gt_T
+        if na == 1:
+            cls_loss = torch.zeros(1)
+            r_acc = torch.zeros(1) + 1
+            pred_R = to_R(y.view(b, nr))
+            l2_loss = (pred_R - true_R).pow(2).mean()
+            loss = self.w * l2_loss
+        elif gt_T is not None and label.ndimension() == 2:
+            wts = wts.view(b, na, na)
+            cls_loss, r_acc = self.classifier(wts, label)
+            confidence, preds = wts.max(1)                                    # best target anchor per source anchor
+            select_R = batched_select_anchor(label, y, to_R)                  # residuals at the labelled pairs
+            pred_res = batched_select_anchor(preds, y, to_R)                  # residuals at the predicted pairs
+            confidence = confidence / (1e-6 + confidence.sum(1, keepdim=True))
+            src = self.anchors[None].expand(b, -1, -1, -1)
+            pred_Rs = torch.einsum("baij,bajk,balk->bail", src, pred_res, self.anchors[preds])
+            pred_R = so3_mean(pred_Rs, confidence)
+            l2_loss = (gt_R - select_R).pow(2).mean()
+            loss = cls_loss + self.w * l2_loss
+        else:
+            wts = wts.view(b, -1)
+            cls_loss, r_acc = self.classifier(wts, label)
+            pred_res = to_R(y.transpose(1, 2).contiguous().view(-1, nr)).view(b, -1, 3, 3)
+            near = (angle_from_R(gt_R.view(-1, 3, 3)).view(b, -1) < self.threshold)[:, :, None, None].float()
+            l2_loss = (gt_R * near - pred_res * near).pow(2).sum()
+            loss = cls_loss + self.w * l2_loss
+            preds = torch.argmax(wts, 1)
+            pred_R = torch.matmul(self.anchors[preds], pred_res[torch.arange(b, device=preds.device), preds])
+        if self.training:
+            self.iter_counter += 1
+        return loss, cls_loss, self.w * l2_loss, r_acc, mean_angular_error(pred_R, true_R)
+
+
+# ------------------------------------------------------------------ 3DMatch descriptors
+def pairwise_distance_matrix(x, y, eps=1e-6):
+    """Euclidean distances between the rows of x [m, c] and y [n, c], squared distances clamped at eps."""
+    d2 = (x * x).sum(1, keepdim=True) + (y * y).sum(1, keepdim=True).t() - 2.0 * torch.matmul(x, y.t())
+    return torch.sqrt(d2.clamp_min(eps))
+
+
+def batch_hard_negative_mining(dist_mat):
+    """Smallest off-diagonal distance of every row."""
+    n = dist_mat.shape[0]
+    assert n == dist_mat.shape[1]
+    off = ~torch.eye(n, dtype=torch.bool, device=dist_mat.device)
+    return dist_mat[off].view(n, n - 1).min(1)[0]
+
+
+class TripletBatchLoss(nn.Module):
+    """Batch-hard triplet loss between matching descriptors src[i] <-> tgt[i]
+    -> (loss, top-1 retrieval accuracy, mean positive distance, mean hardest-negative distance)."""
+
+    def __init__(self, opt, anchors, sigma=2e-1, interpolation="spherical", alpha=0.0):
+        super().__init__()
+        self.register_buffer("anchors", anchors)
+        self.device = opt.device
+        self.loss = opt.train_loss.loss_type
+        self.margin = opt.train_loss.margin
+        self.alpha = alpha
+        self.sigma = sigma
+        self.interpolation = interpolation
+        self.k_precision = 1
+        self.iter_counter = 0
+
+    def forward(self, src, tgt, T, equi_src=None, equi_tgt=None):
+        if self.alpha > 0 and equi_src is not None and equi_tgt is not None:
+            raise NotImplementedError("the equivariance term (alpha > 0, vgtk/vgtk/loss.py:320-358) is not mirrored")
+        return self._forward_invariance(src, tgt)
+
+    def _forward_invariance(self, src, tgt):
+        n = src.shape[0]
+        all_dist = pairwise_distance_matrix(src, tgt)
+        pos = torch.diagonal(all_dist)
+        neg = batch_hard_negative_mining(all_dist)
+        diff = pos - neg
+        if self.loss == "hard":
+            diff = F.relu(diff + self.margin)
+        elif self.loss == "soft":
+            diff = F.softplus(diff, beta=self.margin)
+        elif self.loss == "contrastive":
+            diff = pos + F.relu(self.margin - neg)
+        idx = torch.topk(all_dist, k=self.k_precision, dim=1, largest=False)[1]
+        gt = torch.arange(n, device=idx.device).view(n, 1).expand(-1, self.k_precision)
+        accuracy = (idx == gt).sum().float() / float(n)
+        self.match_idx, self.all_dist, self.fpos, self.cneg = idx, all_dist, pos, neg
+        return diff.mean(), accuracy, pos.mean(), neg.mean()
