@@ -752,3 +752,38 @@ def test_full_size_inv_reg_models_train_one_step(E, which):
     loss.backward()
     missing = [n for n, p in model.named_parameters() if p.grad is None or not bool(torch.isfinite(p.grad).all())]
     assert missing == []
+
+
+# ------------------------------------------------------------ CUDA-graph training step (parallel.GraphedTrainStep)
+def test_graphed_train_step_matches_eager(E):
+    """Two optimisation steps of the classification network replayed from a CUDA graph give the same losses and the
+    same updated weights as the eager loop (up to the order of the fp32 atomics)."""
+    from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
+    from epn_pointcloud_b200.parallel import FlatGradSync, GraphedTrainStep
+    x = sphere(2, 1024, 91).permute(0, 2, 1).contiguous().to(DEV)
+    labels = torch.tensor([5, 31], device=DEV)
+    loss_fn = lambda out, lab: torch.nn.functional.cross_entropy(out[0], lab)  # noqa: E731
+    runs = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        model = ClsSO3ConvModel(cls_model_params(1024, 60)).to(DEV).train()
+        sync = FlatGradSync(model.parameters())
+        opt = torch.optim.SGD(model.parameters(), lr=1e-3)
+        losses = []
+        if mode == "eager":
+            for _ in range(2):
+                sync.zero()
+                loss = loss_fn(model(x), labels)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss))
+        else:
+            step = GraphedTrainStep(model, loss_fn, opt, sync, x, labels, warmup=1)
+            assert step.launches_per_replay > 100
+            for _ in range(2):
+                losses.append(float(step(x, labels)))
+        runs[mode] = (losses, model.backbone[0].blocks[0].inter_conv.conv.basic_conv.W.detach().clone(),
+                      model.outblock.fc2.weight.detach().clone())
+    for a, b_ in zip(runs["graph"][0], runs["eager"][0]):
+        assert abs(a - b_) <= 1e-4 * abs(b_) + 1e-6
+    assert rel_err(runs["graph"][1], runs["eager"][1]) < 1e-4 and rel_err(runs["graph"][2], runs["eager"][2]) < 1e-4
