@@ -60,6 +60,7 @@ c_f = ctypes.c_void_p   # device pointers travel as void*
 c_i = ctypes.c_int
 c_fl = ctypes.c_float
 c_sz = ctypes.c_size_t
+c_u64 = ctypes.c_ulonglong
 
 # name -> (restype, argtypes); mirrors include/epn_b200.h one to one
 SIGNATURES = {
@@ -85,12 +86,12 @@ SIGNATURES = {
     "epn_intra_group_bwd_f32": (c_i, [c_f] * 3 + [c_i] * 5 + [c_f]),
     "epn_inter_so3conv_workspace_bytes": (c_sz, [c_i] * 9),
     "epn_inter_so3conv_grouped_bytes": (c_sz, [c_i] * 6),
-    "epn_inter_so3conv_fwd_f32": (c_i, [c_f] * 6 + [c_fl, c_f, c_f, c_f, c_sz, c_f, c_sz] + [c_i] * 8 + [c_f]),
-    "epn_inter_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_fl, c_f, c_f, c_f, c_f, c_sz, c_f, c_sz] + [c_i] * 8 + [c_f]),
+    "epn_inter_so3conv_fwd_f32": (c_i, [c_f] * 6 + [c_fl, c_f, c_f, c_f, c_sz, c_f, c_sz, c_f] + [c_i] * 8 + [c_f]),
+    "epn_inter_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_fl, c_f, c_f, c_f, c_f, c_sz, c_f, c_sz, c_u64] + [c_i] * 8 + [c_f]),
     "epn_intra_so3conv_workspace_bytes": (c_sz, [c_i] * 7),
     "epn_intra_so3conv_grouped_bytes": (c_sz, [c_i] * 5),
-    "epn_intra_so3conv_fwd_f32": (c_i, [c_f] * 5 + [c_sz, c_f, c_sz] + [c_i] * 6 + [c_f]),
-    "epn_intra_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_sz, c_f, c_sz] + [c_i] * 6 + [c_f]),
+    "epn_intra_so3conv_fwd_f32": (c_i, [c_f] * 5 + [c_sz, c_f, c_sz, c_f] + [c_i] * 6 + [c_f]),
+    "epn_intra_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_sz, c_f, c_sz, c_u64] + [c_i] * 6 + [c_f]),
     "epn_basic_conv_workspace_bytes": (c_sz, [c_i] * 4),
     "epn_basic_conv_fwd_f32": (c_i, [c_f] * 4 + [c_sz] + [c_i] * 4 + [c_f]),
     "epn_basic_conv_bwd_f32": (c_i, [c_f] * 6 + [c_sz] + [c_i] * 4 + [c_f]),

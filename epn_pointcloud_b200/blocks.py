@@ -46,10 +46,15 @@ def norm_act(norm, x, act):
             with torch.no_grad():
                 count = x.numel() // x.shape[1]
                 norm.num_batches_tracked += 1
-                m = norm.momentum if norm.momentum is not None else 1.0 / float(norm.num_batches_tracked)
                 var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))
-                norm.running_mean.mul_(1 - m).add_(stats[0], alpha=m)
-                norm.running_var.mul_(1 - m).add_(var, alpha=m)
+                if norm.momentum is not None:
+                    m = norm.momentum
+                    norm.running_mean.mul_(1 - m).add_(stats[0], alpha=m)
+                    norm.running_var.mul_(1 - m).add_(var, alpha=m)
+                else:  # cumulative moving average: the factor stays on the device (no host sync, graph-capturable)
+                    m = 1.0 / norm.num_batches_tracked.to(torch.float32)
+                    norm.running_mean.add_((stats[0] - norm.running_mean) * m)
+                    norm.running_var.add_((var - norm.running_var) * m)
         return y
     out = norm(x)
     return act(out) if act is not None else out

@@ -71,6 +71,29 @@ struct ProfScope {
 
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: a process that drives several GPUs
+// (model.to('cuda:1'), nn.DataParallel as in vgtk/app/trainer.py:153-160) must set it on each of them.  One
+// DynSmemOnce per launch site remembers, lock-free, on which devices the attribute is already raised; a race
+// between two host threads only repeats an idempotent call.
+struct DynSmemOnce {
+    unsigned long long done[2] = {0ull, 0ull};  // bit d <-> device d (128 devices)
+};
+template <class Kernel>
+inline int ensure_dyn_smem(DynSmemOnce &once, Kernel kernel, int bytes, const char *what) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int w = (dev >> 6) & 1;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&once.done[w], __ATOMIC_ACQUIRE) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("%s: cannot raise dynamic shared memory to %d bytes: %s", what, bytes, cudaGetErrorString(e));
+        return (int)e;
+    }
+    __atomic_fetch_or(&once.done[w], bit, __ATOMIC_RELEASE);
+    return 0;
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // fp32 squared distance pinned to the reference kernels' SASS order

@@ -93,9 +93,8 @@ static SlabPlan plan_slabs(int b, int ck, int p, int na) {
 // Bytes of the forward operand tiles of ALL slabs of one conv call (what a training forward may keep for the
 // weight gradient); 0 when the shape cannot take that route (SIMT backend, or a slab whose column count is
 // not a multiple of the 128-row tile, where padded rows would hold garbage).
-static size_t grouped_tiles_bytes(int b, int ck, int p, int na) {
+static size_t grouped_tiles_bytes(int b, int ck, int p, int na, const SlabPlan &sp) {
     if (gemm_backend() != 0) return 0;
-    const SlabPlan sp = plan_slabs(b, ck, p, na);
     size_t total = 0;
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
@@ -107,6 +106,23 @@ static size_t grouped_tiles_bytes(int b, int ck, int p, int na) {
         }
     }
     return total;
+}
+static size_t grouped_tiles_bytes(int b, int ck, int p, int na) {
+    return grouped_tiles_bytes(b, ck, p, na, plan_slabs(b, ck, p, na));
+}
+
+// "Grouped layout" word: what a forward that kept its operand tiles tells its backward about them -- the order of
+// the K dimension (0 = c*ks+k, 1/2 = the permuted orders of epn_group_direct.cu) and the slab plan -- so that the
+// backward never re-derives either from the process-wide knobs (which may have changed in between).
+//   bits 0-3 K' mode | bits 4-23 clouds per slab | bits 24-55 points per slab
+static unsigned long long encode_layout(int kperm, const SlabPlan &sp) {
+    return (unsigned long long)(kperm & 15) | ((unsigned long long)(sp.bc & 0xFFFFF) << 4) | ((unsigned long long)(unsigned)sp.pc << 24);
+}
+static bool decode_layout(unsigned long long w, int b, int p, int *kperm, SlabPlan *sp) {
+    *kperm = (int)(w & 15);
+    sp->bc = (int)((w >> 4) & 0xFFFFF);
+    sp->pc = (int)((w >> 24) & 0xFFFFFFFFull);
+    return *kperm <= 2 && sp->bc >= 1 && sp->bc <= b && sp->pc >= 1 && sp->pc <= p && (sp->bc == 1 || sp->pc == p);
 }
 
 // Workspace carve-up shared by the three convs.
@@ -372,8 +388,9 @@ EPN_API size_t epn_inter_so3conv_grouped_bytes(int b, int c_in, int p, int nn, i
 EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
                                       const int32_t *idx, const float *anchors, const float *kernels,
                                       float sigma, const float *W, float *out, void *workspace,
-                                      size_t workspace_bytes, void *grouped, size_t grouped_bytes, int b, int c_in,
-                                      int c_out, int p_in, int p, int nn, int na, int ks, void *stream) {
+                                      size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                                      unsigned long long *grouped_layout, int b, int c_in, int c_out, int p_in, int p,
+                                      int nn, int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx); EPN_REQUIRE_PTR(anchors);
     EPN_REQUIRE_PTR(kernels); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
@@ -389,6 +406,10 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     const int kperm = inter_direct(feats, c_in, nn, na, ks);
+    if (grouped != nullptr) {
+        EPN_REQUIRE_PTR(grouped_layout);
+        *grouped_layout = encode_layout(kperm, sp);
+    }
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm));
     if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && sp.pc == p && inter_fused_ok(c_in, c_out, p, nn, na, ks)) {
         // one launch over every cloud: G stays in shared memory; kept tiles (training) keep the slab layout the
@@ -438,8 +459,8 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
                                       const float *centers, const int32_t *idx, const float *anchors,
                                       const float *kernels, float sigma, const float *W, float *dfeats,
                                       float *dW, void *workspace, size_t workspace_bytes, const void *grouped,
-                                      size_t grouped_bytes, int b, int c_in, int c_out, int p_in, int p, int nn,
-                                      int na, int ks, void *stream) {
+                                      size_t grouped_bytes, unsigned long long grouped_layout, int b, int c_in,
+                                      int c_out, int p_in, int p, int nn, int na, int ks, void *stream) {
     EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(xyz); EPN_REQUIRE_PTR(centers); EPN_REQUIRE_PTR(idx);
     EPN_REQUIRE_PTR(anchors); EPN_REQUIRE_PTR(kernels);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p_in); EPN_REQUIRE_POS(p);
@@ -449,10 +470,15 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     EPN_REQUIRE(feats != nullptr || c_in == 1, EPN_ERR_NULL, "feats NULL requires c_in == 1");
     if (dfeats != nullptr) EPN_REQUIRE_PTR(W);
     const int ck = c_in * ks;
-    const SlabPlan sp = plan_slabs(b, ck, p, na);
+    SlabPlan sp = plan_slabs(b, ck, p, na);
+    int kperm_kept = 0;
+    if (grouped != nullptr) {  // slab plan and K order are the forward's, not whatever the knobs say now
+        EPN_REQUIRE(decode_layout(grouped_layout, b, p, &kperm_kept, &sp), EPN_ERR_SHAPE,
+                    "grouped_layout is not a value returned by the forward");
+        EPN_CHECK_GROUPED(inter_group_tiles_ok(nn, na, ks) ? grouped_tiles_bytes(b, ck, p, na, sp) : 0);
+    }
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
-    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
     const uint8_t *keep = static_cast<const uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     if (dfeats != nullptr) {
@@ -484,7 +510,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             if (dW != nullptr && kept != nullptr) {
                 // dW += dout . G with G = the operand tiles the forward kept (K possibly in the permuted order)
-                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s, inter_direct(feats, c_in, nn, na, ks)));
+                EPN_TRY(gemm_dw_grouped(kept, d, c_out, ck, bc, cols, dW, ws, s, kperm_kept));
             } else if (dW != nullptr) {
                 // dW += dout . G^T with G recomputed
                 const float *feats_b = feats ? feats + (size_t)b0 * c_in * p_in * na : nullptr;
@@ -523,7 +549,8 @@ EPN_API size_t epn_intra_so3conv_grouped_bytes(int b, int c_in, int p, int na, i
 
 EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
                                       void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
-                                      int b, int c_in, int c_out, int p, int na, int kn, void *stream) {
+                                      unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
+                                      int kn, void *stream) {
     EPN_REQUIRE_PTR(feats); EPN_REQUIRE_PTR(intra_idx); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
@@ -531,7 +558,11 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
     const SlabPlan sp = plan_slabs(b, ck, p, na);
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
-    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn));
+    if (grouped != nullptr) {
+        EPN_CHECK_GROUPED(epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn));
+        EPN_REQUIRE_PTR(grouped_layout);
+        *grouped_layout = encode_layout(0, sp);
+    }
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s));
@@ -575,18 +606,24 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
 
 EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
                                       const float *W, float *dfeats, float *dW, void *workspace,
-                                      size_t workspace_bytes, const void *grouped, size_t grouped_bytes, int b,
-                                      int c_in, int c_out, int p, int na, int kn, void *stream) {
+                                      size_t workspace_bytes, const void *grouped, size_t grouped_bytes,
+                                      unsigned long long grouped_layout, int b, int c_in, int c_out, int p, int na,
+                                      int kn, void *stream) {
     EPN_REQUIRE_PTR(dout); EPN_REQUIRE_PTR(intra_idx);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
     if (dfeats != nullptr) EPN_REQUIRE_PTR(W);
     if (dW != nullptr && grouped == nullptr) EPN_REQUIRE_PTR(feats);
     const int ck = c_in * kn;
-    const SlabPlan sp = plan_slabs(b, ck, p, na);
+    SlabPlan sp = plan_slabs(b, ck, p, na);
+    if (grouped != nullptr) {
+        int kperm_kept = 0;
+        EPN_REQUIRE(decode_layout(grouped_layout, b, p, &kperm_kept, &sp) && kperm_kept == 0, EPN_ERR_SHAPE,
+                    "grouped_layout is not a value returned by the forward");
+        EPN_CHECK_GROUPED(intra_group_tiles_ok(na, kn) ? grouped_tiles_bytes(b, ck, p, na, sp) : 0);
+    }
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);
-    if (grouped != nullptr) EPN_CHECK_GROUPED(epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn));
     const uint8_t *keep = static_cast<const uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
     if (dfeats != nullptr) EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));

@@ -156,15 +156,8 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
         set_error("umma_dw: n must be a multiple of 128");
         return EPN_ERR_SHAPE;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) {
-            set_error("umma_dw_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_set = true;
-    }
+    static DynSmemOnce once;
+    if (int rc = ensure_dyn_smem(once, umma_dw_kernel, 220 * 1024, "umma_dw_kernel")) return rc;
     DwParams p;
     p.G = static_cast<const uint8_t *>(G_tiles);
     p.B = static_cast<const uint8_t *>(B_tiles);

@@ -586,15 +586,8 @@ int umma_trb_for(int n_rows) {  // rows per B tile = UMMA N: multiple of 16, at 
 
 int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
                      const GemmEpilogue &ep, int split_k, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) {
-            set_error("umma_gemm_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr_set = true;
-    }
+    static DynSmemOnce once;
+    if (int rc = ensure_dyn_smem(once, umma_gemm_kernel, 220 * 1024, "umma_gemm_kernel")) return rc;
     UmmaGemmParams p;
     p.A = static_cast<const uint8_t *>(A_tiles);
     p.B = static_cast<const uint8_t *>(B_tiles);
@@ -641,15 +634,8 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     // column-contiguous outputs (dX: short K loop, 128 KB of output per tile) run persistently: measured
     // 264 -> 167 us per launch; the K-long forward GEMM streams better as two independent CTAs per SM
     if (persistent_on && p.vec && split_k == 1 && total_tiles >= 2LL * sm_count() && total_tiles < (1LL << 31)) {
-        static bool attr2 = false;
-        if (!attr2) {
-            cudaError_t e = cudaFuncSetAttribute(umma_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-            if (e != cudaSuccess) {
-                set_error("umma_gemm_persistent_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-                return (int)e;
-            }
-            attr2 = true;
-        }
+        static DynSmemOnce once2;
+        if (int rc = ensure_dyn_smem(once2, umma_gemm_persistent_kernel, 226 * 1024, "umma_gemm_persistent_kernel")) return rc;
         const int gw = trb < 128 ? trb : 128;
         const size_t stg_bytes = p.vec ? (size_t)4 * 32 * (gw + 4) * sizeof(float) : 0;  // staged bulk-store epilogue (dX)
         const size_t avail = (size_t)226 * 1024 - 512 - stg_bytes;
@@ -724,15 +710,8 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
     SplitSrc src{dout, (long long)p * 60, dout_stride_z, 1, 1LL << 60, 0, dout_stride_o};
     int rc = launch_split_tiles(src, dout_tiles, n, c_k, 240, s);
     if (rc) return rc;
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(umma_gemm_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
-        if (e != cudaSuccess) {
-            set_error("umma_gemm_persistent_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr = true;
-    }
+    static DynSmemOnce once3;
+    if (int rc3 = ensure_dyn_smem(once3, umma_gemm_persistent_kernel, 226 * 1024, "umma_gemm_persistent_kernel")) return rc3;
     UmmaGemmParams q;
     q.A = static_cast<const uint8_t *>(wt_tiles);
     q.B = static_cast<const uint8_t *>(dout_tiles);

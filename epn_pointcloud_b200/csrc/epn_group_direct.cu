@@ -407,14 +407,11 @@ int launch_inter_group_direct(const float *feats, const int32_t *idx, const Inte
                               int ks, cudaStream_t s) {
     const int mode = inter_group_direct_mode(feats, c, nn, na, ks);
     if (mode == 0 || bc > 65535) return 1;
-    static bool set = false;
+    static DynSmemOnce once1, once2;
     const size_t smem1 = (size_t)(GD_NN * 6 + 2 * GD_CCH * GD_NN * GD_NA) * sizeof(float);
     const size_t smem2 = (size_t)(G3_NN * 6 + 2 * G3_CCH * G3_NN * GD_NA) * sizeof(float);
-    if (!set) {
-        cudaFuncSetAttribute(inter_group_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
-        cudaFuncSetAttribute(inter_group_direct32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-        set = true;
-    }
+    if (int rc = ensure_dyn_smem(once1, inter_group_direct_kernel, (int)smem1, "inter_group_direct_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once2, inter_group_direct32_kernel, (int)smem2, "inter_group_direct32_kernel")) return rc;
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_GROUP);
     if (mode == 1)

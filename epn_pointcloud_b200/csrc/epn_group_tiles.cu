@@ -244,11 +244,8 @@ template <int NN, int KG, int CCH, int NA, bool HAS_FEATS>
 static int launch_variant(const float *feats, const int32_t *idx, const InterGeom &g, const TileOut &o, dim3 grid, int c,
                           int p_in, int p, int nn, int p_off, cudaStream_t s) {
     const size_t smem = (size_t)(NN * 6 + 2 * CCH * NN * NA + CCH * GT_KS * (NA + 1)) * sizeof(float);
-    static bool set = false;
-    if (!set) {
-        cudaFuncSetAttribute(inter_group_tiles_kernel<NN, KG, CCH, NA, HAS_FEATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        set = true;
-    }
+    static DynSmemOnce once;  // one per template instantiation
+    if (int rc = ensure_dyn_smem(once, inter_group_tiles_kernel<NN, KG, CCH, NA, HAS_FEATS>, (int)smem, "inter_group_tiles_kernel")) return rc;
     inter_group_tiles_kernel<NN, KG, CCH, NA, HAS_FEATS><<<grid, GT_LANES *(GT_KS / KG), smem, s>>>(feats, idx, g, o, c, p_in, p, nn, p_off);
     return check_launch("inter_group_tiles_kernel");
 }

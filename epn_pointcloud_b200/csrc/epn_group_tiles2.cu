@@ -274,12 +274,9 @@ int launch_inter_scatter(const float *dG, long long stride_b, long long stride_c
         return 1;
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_SCATTER);
-    static bool set = false;
-    if (!set) {
-        cudaFuncSetAttribute(inter_scatter_kernel<16, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-        cudaFuncSetAttribute(inter_scatter_kernel<32, 60>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-        set = true;
-    }
+    static DynSmemOnce once16, once32;
+    if (int rc = ensure_dyn_smem(once16, inter_scatter_kernel<16, 60>, 80 * 1024, "inter_scatter_kernel<16>")) return rc;
+    if (int rc = ensure_dyn_smem(once32, inter_scatter_kernel<32, 60>, 80 * 1024, "inter_scatter_kernel<32>")) return rc;
     if (nn <= 16) {
         const size_t smem = (size_t)(16 * 6 + SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<16, 60><<<grid, SC_LANES * (16 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,

@@ -366,16 +366,8 @@ int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     if (nst > 8) nst = 8;
     P.nst = nst;
     const size_t smem_bytes = fixed + (size_t)nst * stage;
-    static bool set = false;
-    if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(inter_fused_kernel<NN, KG, CCH, PTS, HAS_FEATS>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024);
-        if (e != cudaSuccess) {
-            set_error("inter_fused_kernel: cannot raise dynamic smem: %s", cudaGetErrorString(e));
-            return (int)e;
-        }
-        set = true;
-    }
+    static DynSmemOnce once;  // one per template instantiation
+    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<NN, KG, CCH, PTS, HAS_FEATS>, 227 * 1024 - 1024, "inter_fused_kernel")) return rc;
     dim3 grid(p_cnt / PTS, bc);
     inter_fused_kernel<NN, KG, CCH, PTS, HAS_FEATS><<<grid, NPROD + 128, smem_bytes, s>>>(P);
     return check_launch("inter_fused_kernel");

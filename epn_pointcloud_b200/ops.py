@@ -8,6 +8,7 @@ order and return shapes of the reference's pybind modules `vgtk.cuda.grouping`
 (vgtk/vgtk/cuda/grouping_cuda.cpp:176-181), `vgtk.cuda.gathering`
 (gathering_cuda.cpp:61-65) and `vgtk.cuda.zpconv` (zpconv_cuda.cpp:112-118).
 """
+import ctypes
 import types
 
 import torch
@@ -290,6 +291,31 @@ def _grouped_buffer(nbytes, device, keep_grouped):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
+class _Grouped:
+    """The operand tiles a training forward kept (uint8 device buffer) together with the layout word the
+    library returned for them (K order + slab plan); the backward gets both back, so the pair stays consistent
+    whatever happens to the process-wide knobs in between."""
+
+    __slots__ = ("buf", "layout")
+
+    def __init__(self, buf, layout):
+        self.buf, self.layout = buf, int(layout)
+
+    @staticmethod
+    def wrap(buf, layout):
+        return None if buf is None else _Grouped(buf, layout)
+
+    @staticmethod
+    def args(g):
+        """(pointer, bytes, layout) arguments of a backward call."""
+        if g is None:
+            return None, 0, 0
+        return g.buf.data_ptr(), g.buf.numel(), g.layout
+
+    def numel(self):
+        return self.buf.numel()
+
+
 _KEEP_FRACTION = 0.25
 _keep_mode = None
 
@@ -334,11 +360,13 @@ def inter_so3conv_fwd(feats, xyz, centers, idx, anchors, kernels, sigma, W, keep
         ws = _workspace(wsb, xyz.device)
         grouped = _grouped_buffer(L.epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks) if keep_grouped else 0,
                                   xyz.device, keep_grouped)
+        layout = ctypes.c_ulonglong(0)
         _lib.check(L.epn_inter_so3conv_fwd_f32(_p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors), _p(kernels),
                                                float(sigma), _p(W), _p(out), _p(ws), wsb, _p(grouped),
-                                               0 if grouped is None else grouped.numel(), b, c_in, c_out, p_in, p, nn,
-                                               na, ks, _stream()), "epn_inter_so3conv_fwd_f32")
-    return (out, grouped) if keep_grouped else out
+                                               0 if grouped is None else grouped.numel(), ctypes.addressof(layout),
+                                               b, c_in, c_out, p_in, p, nn, na, ks, _stream()),
+                   "epn_inter_so3conv_fwd_f32")
+    return (out, _Grouped.wrap(grouped, layout.value)) if keep_grouped else out
 
 
 def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W, need_dfeats=True, need_dw=True,
@@ -358,7 +386,7 @@ def inter_so3conv_bwd(dout, feats, xyz, centers, idx, anchors, kernels, sigma, W
         ws = _workspace(wsb, dout.device)
         _lib.check(L.epn_inter_so3conv_bwd_f32(_p(dout), _p(feats), _p(xyz), _p(centers), _p(idx), _p(anchors),
                                                _p(kernels), float(sigma), _p(W), _p(dfeats), _p(dW), _p(ws), wsb,
-                                               _p(grouped), 0 if grouped is None else grouped.numel(), b,
+                                               *_Grouped.args(grouped), b,
                                                c_in, c_out, p_in, p, nn, na, ks, _stream()),
                    "epn_inter_so3conv_bwd_f32")
     return dfeats, dW
@@ -380,10 +408,11 @@ def intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=False):
         ws = _workspace(wsb, feats.device)
         grouped = _grouped_buffer(L.epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn) if keep_grouped else 0,
                                   feats.device, keep_grouped)
+        layout = ctypes.c_ulonglong(0)
         _lib.check(L.epn_intra_so3conv_fwd_f32(_p(feats), _p(intra_idx), _p(W), _p(out), _p(ws), wsb, _p(grouped),
-                                               0 if grouped is None else grouped.numel(), b, c_in, c_out,
-                                               p, na, kn, _stream()), "epn_intra_so3conv_fwd_f32")
-    return (out, grouped) if keep_grouped else out
+                                               0 if grouped is None else grouped.numel(), ctypes.addressof(layout),
+                                               b, c_in, c_out, p, na, kn, _stream()), "epn_intra_so3conv_fwd_f32")
+    return (out, _Grouped.wrap(grouped, layout.value)) if keep_grouped else out
 
 
 def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True, grouped=None):
@@ -398,7 +427,7 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True,
         wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 1)
         ws = _workspace(wsb, feats.device)
         _lib.check(L.epn_intra_so3conv_bwd_f32(_p(dout), _p(feats), _p(intra_idx), _p(W), _p(dfeats), _p(dW), _p(ws),
-                                               wsb, _p(grouped), 0 if grouped is None else grouped.numel(), b, c_in,
+                                               wsb, *_Grouped.args(grouped), b, c_in,
                                                c_out, p, na, kn, _stream()),
                    "epn_intra_so3conv_bwd_f32")
     return dfeats, dW

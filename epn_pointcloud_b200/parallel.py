@@ -37,22 +37,43 @@ class FlatGradSync:
             p.grad = self.flat[off:off + n].view_as(p)
             off += n
 
+        self._views = [p.grad for p in self.params]
+
     def zero(self):
         self.flat.zero_()
 
-    def all_reduce_mean(self):
-        """Sum over ranks then divide by the world size; no-op for a single process."""
+    def rebind(self):
+        """Point every parameter's .grad back at its slice of the flat buffer.  `optimizer.zero_grad()` (default
+        set_to_none=True) or `model.zero_grad()` drop the views: the next backward would then allocate private
+        gradients that neither the all-reduce nor a graph replay writing into the flat buffer would see.  A private
+        gradient that already holds data is copied in, so nothing is lost."""
+        for p, v in zip(self.params, self._views):
+            g = p.grad
+            if g is None:
+                p.grad = v
+            elif g.data_ptr() != v.data_ptr():
+                v.copy_(g)
+                p.grad = v
+
+    def all_reduce_mean(self, local_units=None):
+        """Sum over ranks then divide; no-op for a single process.  With `local_units` (clouds this rank's loss
+        was averaged over) the result is the gradient of the mean over ALL clouds even when the shards are not
+        equal (shard_range with a remainder); without it the shards are assumed equal (mean of per-rank means)."""
+        self.rebind()
         if not (dist.is_available() and dist.is_initialized()):
             return
         ws = dist.get_world_size(self.group)
         if ws == 1:
             return
-        for p in self.params:  # a backward pass may have re-bound .grad: copy stragglers back
-            if p.grad is not None and p.grad.data_ptr() < self.flat.data_ptr() or \
-               p.grad is not None and p.grad.data_ptr() >= self.flat.data_ptr() + self.flat.numel() * self.flat.element_size():
-                raise RuntimeError("parameter gradient left the flat buffer")
+        if local_units is None:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / ws)
+            return
+        n = torch.tensor([float(local_units)], dtype=self.flat.dtype, device=self.flat.device)
+        self.flat.mul_(n)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM, group=self.group)
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.mul_(1.0 / ws)
+        self.flat.div_(n)
 
 
 class GraphedTrainStep:
@@ -77,6 +98,11 @@ class GraphedTrainStep:
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
+        # the warm-up passes and the capture pass run the model in its current mode on the example batch: module
+        # buffers they would advance (BatchNorm running statistics, num_batches_tracked) and the RNG state are
+        # snapshotted and restored, so constructing the step leaves the model as it found it
+        buffers = [(b, b.detach().clone()) for b in model.buffers()]
+        rng = torch.cuda.get_rng_state(self.x.device)
         with torch.cuda.stream(side):   # warm-up off the default stream: lazy initialisations, allocator pools
             for _ in range(max(int(warmup), 1)):
                 self._fwd_bwd()
@@ -88,8 +114,14 @@ class GraphedTrainStep:
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
         self.launches_per_replay = int(_lib.lib().epn_launch_count() - n0)  # this library's kernels inside the graph
+        with torch.no_grad():
+            for b, saved in buffers:
+                b.copy_(saved)
+        torch.cuda.set_rng_state(rng, self.x.device)
+        sync.zero()
 
     def _fwd_bwd(self):
+        self.sync.rebind()
         self.sync.zero()
         loss = self.loss_fn(self.model(self.x), self.labels)
         loss.backward()

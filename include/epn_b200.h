@@ -9,8 +9,20 @@
  *
  * Conventions
  *   - all pointers are DEVICE pointers owned by the caller; the library never
- *     allocates, frees or keeps device memory, and holds no global state
- *     except a thread-local error string;
+ *     allocates, frees or keeps device memory.  No call leaves per-call state
+ *     behind: what a forward must tell its backward travels through the caller
+ *     (`grouped` buffer + `grouped_layout` word).  Process-wide state is limited
+ *     to (a) a thread-local error string, (b) a launch counter and the optional
+ *     profiling record, (c) the CONFIGURATION KNOBS at the end of this header
+ *     (epn_set_gemm_backend / epn_set_slab_bytes / epn_set_fused_inter and their
+ *     EPN_* environment defaults): atomics read once at the start of every call,
+ *     shared by all threads and devices of the process.  Calls are re-entrant and
+ *     thread-safe; changing a knob while another thread is inside a call is
+ *     allowed and affects only calls that start afterwards;
+ *   - the per-device kernel attributes (dynamic shared memory limits) are set
+ *     lazily on every device the library is used on (one process may drive
+ *     several GPUs, as the reference's nn.DataParallel does,
+ *     vgtk/vgtk/app/trainer.py:153-160);
  *   - tensors are dense, row-major, in the reference's layouts:
  *       xyz [B,3,P]   feats [B,C,P,A] (A innermost)   idx [B,P,K] int32
  *       inter_w [B,P,A,KS,K]   grouped [B,C,KS,P,A]   W [C_out, C_in*KS]
@@ -31,7 +43,7 @@
 extern "C" {
 #endif
 
-#define EPN_B200_VERSION 100 /* major*1000 + minor */
+#define EPN_B200_VERSION 101 /* major*1000 + minor */
 
 #define EPN_ERR_NULL (-1)     /* required pointer is NULL              */
 #define EPN_ERR_SHAPE (-2)    /* non-positive or unsupported extent    */
@@ -144,24 +156,27 @@ int epn_intra_group_bwd_f32(const float *dout, const int32_t *intra_idx, float *
  * A training forward may pass a buffer of exactly epn_*_grouped_bytes(...) bytes (256-B aligned); the
  * tensor-core operand tiles of the grouped tensor are then written there instead of into the workspace, and
  * a backward given the same buffer computes dW from them without re-running the spatial contraction.
- * epn_*_grouped_bytes returns 0 when the shape / backend cannot do that (then pass NULL).  The slab size
- * (epn_set_slab_bytes) and GEMM backend must not change between that forward and its backward. */
+ * epn_*_grouped_bytes returns 0 when the shape / backend cannot do that (then pass NULL).
+ * grouped_layout: a forward given `grouped` stores one word describing how it laid the tiles out (order of the
+ * K dimension, slab plan); the caller hands that word to the backward together with the buffer, so the pair
+ * stays consistent even if the configuration knobs change between the two calls.  Ignored when grouped == NULL. */
 size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int p_in, int p, int nn, int na,
                                          int ks, int backward);
 size_t epn_inter_so3conv_grouped_bytes(int b, int c_in, int p, int nn, int na, int ks);
 int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, const float *centers,
                               const int32_t *idx, const float *anchors, const float *kernels,
                               float sigma, const float *W, float *out, void *workspace,
-                              size_t workspace_bytes, void *grouped, size_t grouped_bytes, int b, int c_in,
-                              int c_out, int p_in, int p, int nn, int na, int ks, void *stream);
+                              size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                              unsigned long long *grouped_layout, int b, int c_in, int c_out, int p_in, int p,
+                              int nn, int na, int ks, void *stream);
 /* dout [b,c_out,p,na] -> dfeats [b,c_in,p_in,na] (NULL to skip; else fully
  * written) and dW [c_out,c_in*ks] (NULL to skip; else fully written). */
 int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, const float *xyz,
                               const float *centers, const int32_t *idx, const float *anchors,
                               const float *kernels, float sigma, const float *W, float *dfeats,
                               float *dW, void *workspace, size_t workspace_bytes, const void *grouped,
-                              size_t grouped_bytes, int b, int c_in, int c_out, int p_in, int p, int nn,
-                              int na, int ks, void *stream);
+                              size_t grouped_bytes, unsigned long long grouped_layout, int b, int c_in,
+                              int c_out, int p_in, int p, int nn, int na, int ks, void *stream);
 
 /* IntraSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:197-200):
  *   out[b,o,p,a] = sum_{c,k} W[o,c*kn+k] * feats[b,c,p,intra_idx[a,k]] */
@@ -170,12 +185,14 @@ size_t epn_intra_so3conv_workspace_bytes(int b, int c_in, int c_out, int p, int 
 size_t epn_intra_so3conv_grouped_bytes(int b, int c_in, int p, int na, int kn);
 int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
                               void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
-                              int b, int c_in, int c_out, int p, int na, int kn, void *stream);
+                              unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
+                              int kn, void *stream);
 /* feats may be NULL when grouped is given (dW then needs nothing else). */
 int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
                               const float *W, float *dfeats, float *dW, void *workspace,
-                              size_t workspace_bytes, const void *grouped, size_t grouped_bytes, int b,
-                              int c_in, int c_out, int p, int na, int kn, void *stream);
+                              size_t workspace_bytes, const void *grouped, size_t grouped_bytes,
+                              unsigned long long grouped_layout, int b, int c_in, int c_out, int p, int na,
+                              int kn, void *stream);
 
 /* BasicSO3Conv.forward (vgtk/vgtk/so3conv/modules.py:48-55) on an already
  * grouped tensor: x [b, ck, pa], W [co, ck] -> out [b, co, pa].
@@ -204,12 +221,13 @@ int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *gamma, co
                          const float *stats, float *dx, float *dgamma, float *dbeta, void *workspace,
                          size_t workspace_bytes, int b, int c, int n, int mode, float slope, void *stream);
 
-/* Channel-GEMM engine used by the three convs: 0 = tcgen05 tensor cores with bf16 hi/lo
+/* ------------------------------------------------ configuration knobs (PROCESS-GLOBAL, see Conventions)
+ * Channel-GEMM engine used by the three convs: 0 = tcgen05 tensor cores with bf16 hi/lo
  * operand splitting (default; fp32-faithful to ~1e-5 relative), 1 = fp32 SIMT GEMM (the
  * in-library cross-check used by the GPU tests; also selectable with EPN_GEMM=simt). */
 void epn_set_gemm_backend(int simt);
-/* Size of the L2-resident grouped slab the convs are scheduled in (default 32 MiB, or the
- * EPN_SLAB_BYTES environment variable).  Changes the *_workspace_bytes() results. */
+/* Upper bound of the grouped tensor one slab of a conv call may hold (default 1 GiB, or the
+ * EPN_SLAB_BYTES environment variable).  Changes the *_workspace_bytes() / *_grouped_bytes() results. */
 void epn_set_slab_bytes(size_t bytes);
 size_t epn_get_slab_bytes(void);
 int epn_get_gemm_backend(void);

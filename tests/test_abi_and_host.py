@@ -37,7 +37,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 def test_version_and_argument_errors_without_gpu():
     from epn_pointcloud_b200 import _lib
     L = _lib.lib()
-    assert L.epn_version() == 100
+    assert L.epn_version() == 101
     # NULL pointers and bad extents are rejected before anything touches a device
     rc = L.epn_ball_query_f32(None, None, None, 1, 8, 8, 0.1, 4, None)
     assert rc == -1 and b"NULL" in L.epn_last_error()
@@ -45,7 +45,7 @@ def test_version_and_argument_errors_without_gpu():
     p = ctypes.cast(buf, ctypes.c_void_p)
     rc = L.epn_ball_query_f32(p, p, p, 0, 8, 8, 0.1, 4, None)
     assert rc == -2 and b"must be > 0" in L.epn_last_error()
-    rc = L.epn_inter_so3conv_fwd_f32(None, p, p, p, p, p, 0.1, p, p, p, 16, None, 0, 1, 4, 4, 8, 8, 4, 60, 24, None)
+    rc = L.epn_inter_so3conv_fwd_f32(None, p, p, p, p, p, 0.1, p, p, p, 16, None, 0, None, 1, 4, 4, 8, 8, 4, 60, 24, None)
     assert rc == -1  # feats NULL with c_in != 1
     # kept operand tiles: one 128-row tile per 128 grouped columns, 4 bytes (bf16 hi+lo) per element, and
     # only for shapes the tile kernels cover with whole tiles
@@ -105,6 +105,23 @@ ref.load_state_dict(model.state_dict())
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
     assert p.grad.data_ptr() >= sync.flat.data_ptr()
+# optimizer.zero_grad() (set_to_none=True) drops the flat views: the next all-reduce must still see every gradient
+model.zero_grad(set_to_none=True)
+assert all(p.grad is None for p in model.parameters())
+model(x[lo:hi]).pow(2).sum().backward()           # autograd allocates private gradients
+sync.all_reduce_mean()
+for p, q in zip(model.parameters(), ref.parameters()):
+    assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6)
+    assert sync.flat.data_ptr() <= p.grad.data_ptr() < sync.flat.data_ptr() + sync.flat.numel() * 4
+# unequal shards (7 clouds over 2 ranks = 4 + 3): per-rank MEAN losses, weighted by the shard sizes
+lo, hi = shard_range(7, dist.get_rank(), 2)
+sync.rebind(); sync.zero()
+model(x[lo:hi]).pow(2).sum(1).mean().backward()
+sync.all_reduce_mean(local_units=hi - lo)
+ref.zero_grad()
+ref(x[:7]).pow(2).sum(1).mean().backward()
+for p, q in zip(model.parameters(), ref.parameters()):
+    assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
 dist.destroy_process_group()
 print("ok")
 """

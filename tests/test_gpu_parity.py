@@ -397,7 +397,7 @@ def test_error_behaviour_on_device(E):
     with pytest.raises(RuntimeError):
         E.ops.ball_query(x.permute(0, 2, 1), x, 0.1, 4)  # non-contiguous
     rc = L.epn_inter_so3conv_fwd_f32(None, x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), x.data_ptr(), 0.1,
-                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, None, 0, 1, 1, 4, 8, 8, 4, 60, 24, None)
+                                     x.data_ptr(), x.data_ptr(), x.data_ptr(), 16, None, 0, None, 1, 1, 4, 8, 8, 4, 60, 24, None)
     assert rc == -3 and b"workspace" in L.epn_last_error()
     # a kept-tiles buffer of the wrong size, or for a shape without whole tiles, is refused
     f = torch.zeros(1, 4, 64, 60, device=DEV)
@@ -407,7 +407,7 @@ def test_error_behaviour_on_device(E):
     wsb = L.epn_intra_so3conv_workspace_bytes(1, 4, 8, 64, 60, 12, 0)
     ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
     rc = L.epn_intra_so3conv_fwd_f32(f.data_ptr(), idx.data_ptr(), W.data_ptr(), out.data_ptr(), ws.data_ptr(), wsb,
-                                     ws.data_ptr(), 1024, 1, 4, 8, 64, 60, 12, None)
+                                     ws.data_ptr(), 1024, None, 1, 4, 8, 64, 60, 12, None)
     assert rc == -3 and b"grouped_bytes" in L.epn_last_error()
 
 
