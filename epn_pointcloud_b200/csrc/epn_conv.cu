@@ -43,13 +43,17 @@ static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused
     return v;
 }
 
-// Inter grouping with the bf16 split in registers + permuted K order (epn_group_direct.cu); EPN_DIRECT=0 keeps the
-// staging-tile kernel.  Forward and backward must agree, so the decision is a pure function of the call's shape.
-static int inter_direct(const float *feats, int c_in, int nn, int na, int ks) {  // 0 or the K' mode
-    static const int on = getenv("EPN_DIRECT") ? atoi(getenv("EPN_DIRECT")) : 3;  // bit 0: K <= 16 kernel, bit 1: K <= 32 kernel
-    if (gemm_backend() != 0 || fused_enabled()) return 0;
-    const int mode = inter_group_direct_mode(feats, c_in, nn, na, ks);
-    return (mode && (on & (1 << (mode - 1)))) ? mode : 0;
+// Inter grouping with the bf16 split in registers + permuted K order (epn_group_direct.cu): 0 or the K' mode the
+// forward will use for this call (the backward is told through the grouped_layout word, never re-derives it).
+static int inter_direct(const float *feats, int c_in, int nn, int na, int ks) {
+    if (gemm_backend() != 0 || fused_enabled() || c_in == 1) return 0;
+    return inter_group_direct_mode(feats, c_in, nn, na, ks);
+}
+
+// Shapes whose forward writes operand tiles directly (and can therefore keep them for the weight gradient).
+static bool inter_tiles_available(int c_in, int nn, int na, int ks) {
+    if (c_in == 1) return inter_group_occ_ok(c_in, nn, na, ks);
+    return inter_group_tiles_ok(nn, na, ks) || inter_group_direct_mode(reinterpret_cast<const float *>(16), c_in, nn, na, ks) != 0;
 }
 
 static std::atomic<size_t> g_slab_bytes{0};
@@ -381,7 +385,7 @@ EPN_API size_t epn_inter_so3conv_workspace_bytes(int b, int c_in, int c_out, int
 }
 
 EPN_API size_t epn_inter_so3conv_grouped_bytes(int b, int c_in, int p, int nn, int na, int ks) {
-    if (b <= 0 || c_in <= 0 || p <= 0 || nn <= 0 || na <= 0 || ks <= 0 || !inter_group_tiles_ok(nn, na, ks)) return 0;
+    if (b <= 0 || c_in <= 0 || p <= 0 || nn <= 0 || na <= 0 || ks <= 0 || !inter_tiles_available(c_in, nn, na, ks)) return 0;
     return grouped_tiles_bytes(b, c_in * ks, p, na);
 }
 
@@ -432,7 +436,11 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             void *tiles = keep ? keep : ws.tilesA;  // kept tiles: every slab has its own region
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;  // 0: the grouping kernel wrote the operand tiles itself
-            if (kperm) {
+            if (c_in == 1 && gemm_backend() == 0 && inter_group_occ_ok(c_in, nn, na, ks)) {
+                direct = launch_inter_group_occ(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cols, p0, pc, bc, p_in, p, nn, na,
+                                                ks, s);
+                if (direct != 0) return direct == 1 ? EPN_ERR_SHAPE : direct;
+            } else if (kperm) {
                 direct = launch_inter_group_direct(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cdiv(ck, 32), cols, p0, pc, bc,
                                                    c_in, p_in, p, nn, na, ks, s);
                 if (direct != 0) return direct == 1 ? EPN_ERR_SHAPE : direct;
@@ -475,7 +483,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     if (grouped != nullptr) {  // slab plan and K order are the forward's, not whatever the knobs say now
         EPN_REQUIRE(decode_layout(grouped_layout, b, p, &kperm_kept, &sp), EPN_ERR_SHAPE,
                     "grouped_layout is not a value returned by the forward");
-        EPN_CHECK_GROUPED(inter_group_tiles_ok(nn, na, ks) ? grouped_tiles_bytes(b, ck, p, na, sp) : 0);
+        EPN_CHECK_GROUPED(inter_tiles_available(c_in, nn, na, ks) ? grouped_tiles_bytes(b, ck, p, na, sp) : 0);
     }
     const Workspace ws = carve(workspace, ck, c_out, (long long)sp.bc * sp.pc * na, true);
     EPN_CHECK_WS(ws.total);

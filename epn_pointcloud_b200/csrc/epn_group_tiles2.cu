@@ -10,6 +10,7 @@
 // Both are specialised for the shipped geometry (60 anchors, 12 intra neighbours, 24 kernel points) so
 // all shared-memory strides and index decodes are compile-time constants; other shapes fall back to the
 // generic kernels of epn_group.cu.
+#include "epn_dedup.cuh"
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
@@ -134,51 +135,28 @@ __global__ void __launch_bounds__(SC_LANES *(NN / SC_NB), NN == 16 ? 2 : 1)
 inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long stride_ck, const int32_t *__restrict__ idx,
                      InterGeom g, float *__restrict__ dfeats, int c, int p_in, int p, int nn, int p_off) {
     constexpr int NTHR = SC_LANES * (NN / SC_NB);
+    // NN == 16: rows of <= 16 slots, one CTA per point.  NN == 32: rows of up to DEDUP_MAX_RAW slots; the scatter is
+    // additive over neighbours, so CTA blockIdx.z takes the distinct neighbours [32 z, 32 z + 32) of the point and
+    // CTAs beyond the point's distinct count leave at once (the K = 64 layers of the rotation / 3DMatch models).
+    constexpr int CAP = NN == 16 ? 16 : DEDUP_MAX_RAW;
     extern __shared__ __align__(16) float s_dyn[];
-    float *s_g = s_dyn;                                            // [NN][3]  distinct neighbour offsets
-    int32_t *s_idx = reinterpret_cast<int32_t *>(s_dyn + NN * 3);  // [NN]     distinct neighbour indices
-    float *s_mult = s_dyn + NN * 4;                                // [NN]     multiplicities
-    int32_t *s_raw = reinterpret_cast<int32_t *>(s_dyn + NN * 5);  // [NN]     ball-query row as stored
-    float *Ds = s_dyn + NN * 6;                                    // [SC_BUFS][SC_CCH*24][NA]
-    __shared__ int s_nu;
+    float *Ds = s_dyn;                                             // [SC_BUFS][SC_CCH*24][NA]
+    __shared__ NeighbourList<CAP> L;
     const int tid = threadIdx.x;
     const int a = tid % SC_LANES, grp = tid / SC_LANES;
-    const int n0 = grp * SC_NB;
+    const int n0 = (int)blockIdx.z * NN + grp * SC_NB;
     const bool a_ok = a < NA;
     const int aa = a_ok ? a : a - 4;  // dead lanes shadow a live lane of their own warp (broadcast, no bank conflict)
     const int z = blockIdx.y, pl = blockIdx.x, pi = p_off + pl;
     float *DF = dfeats + (size_t)z * c * p_in * NA;
 
-    // distinct neighbours + multiplicities (see inter_group_tiles_kernel): one RED per distinct neighbour
-    for (int n = tid; n < NN; n += NTHR) s_raw[n] = n < nn ? idx[((size_t)z * p + pi) * nn + n] : -1;
-    __syncthreads();
-    if (tid < 32) {
-        const int n = tid;
-        const int q = n < nn ? s_raw[n] : -1;
-        bool uniq = n < nn;
-        for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
-        int mult = 0;
-        for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
-        const unsigned mask = __ballot_sync(0xffffffffu, uniq);
-        const int pos = __popc(mask & ((1u << n) - 1u));
-        if (uniq) {
-            const float *X = g.xyz + (size_t)z * 3 * p_in;
-            const float *Cn = g.centers + (size_t)z * 3 * p;
-            s_idx[pos] = q;
-            s_mult[pos] = (float)mult;
-            s_g[pos * 3] = X[q] - Cn[pi];
-            s_g[pos * 3 + 1] = X[p_in + q] - Cn[p + pi];
-            s_g[pos * 3 + 2] = X[2 * p_in + q] - Cn[2 * p + pi];
-        }
-        const int cnt = __popc(mask);
-        if (n >= cnt && n < NN) {
-            s_idx[n] = 0; s_mult[n] = 0.f;
-            s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
-        }
-        if (n == 0) s_nu = cnt;
-    }
-    __syncthreads();
-    nn = s_nu;  // number of DISTINCT neighbours
+    // distinct neighbours + multiplicities: one RED per distinct neighbour
+    dedup_row(L, idx + ((size_t)z * p + pi) * nn, nn, g.xyz + (size_t)z * 3 * p_in, g.centers + (size_t)z * 3 * p, p_in, p, pi,
+              tid, NTHR, [] { __syncthreads(); });
+    const float *s_g = L.g, *s_mult = L.mult;
+    const int32_t *s_idx = L.idx;
+    nn = L.total;  // number of DISTINCT neighbours
+    if ((int)blockIdx.z * NN >= nn) return;  // CTA-uniform
     const bool grp_active = n0 < nn;  // warp-uniform: this thread's 4 neighbours exist
 
     uint64_t w2[SC_KS][SC_NB / 2];  // (neighbour 2j, neighbour 2j+1) pairs for the fp32x2 FMAs
@@ -269,20 +247,20 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
 int launch_inter_scatter(const float *dG, long long stride_b, long long stride_ck, const int32_t *idx,
                          const InterGeom &g, float *dfeats, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn,
                          int na, int ks, cudaStream_t s) {
-    if (ks != SC_KS || nn > 32 || na != 60 || bc > 65535 || (stride_ck % 4) != 0 || (stride_b % 4) != 0 ||
+    if (ks != SC_KS || nn > DEDUP_MAX_RAW || na != 60 || bc > 65535 || (stride_ck % 4) != 0 || (stride_b % 4) != 0 ||
         ((uintptr_t)dG & 15) != 0 || (long long)p_in * na >= (1LL << 31))
         return 1;
-    dim3 grid(p_cnt, bc);
+    dim3 grid(p_cnt, bc, nn <= 32 ? 1 : (nn + 31) / 32);
     ProfScope prof(s, KC_INTER_SCATTER);
     static DynSmemOnce once16, once32;
     if (int rc = ensure_dyn_smem(once16, inter_scatter_kernel<16, 60>, 80 * 1024, "inter_scatter_kernel<16>")) return rc;
     if (int rc = ensure_dyn_smem(once32, inter_scatter_kernel<32, 60>, 80 * 1024, "inter_scatter_kernel<32>")) return rc;
     if (nn <= 16) {
-        const size_t smem = (size_t)(16 * 6 + SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<16, 60><<<grid, SC_LANES * (16 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     } else {
-        const size_t smem = (size_t)(32 * 6 + SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
+        const size_t smem = (size_t)(SC_BUFS * SC_CCH * SC_KS * 60) * sizeof(float);
         inter_scatter_kernel<32, 60><<<grid, SC_LANES * (32 / SC_NB), smem, s>>>(dG, stride_b, stride_ck, idx, g, dfeats, c,
                                                                                p_in, p, nn, p_off);
     }

@@ -89,7 +89,7 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
 
 // epn_group_direct.cu -- inter grouping with the bf16 split in registers; the operand tiles use a permuted K order
 // (24 kernel points):  mode 1 (K <= 16 neighbours, c % 4 == 0)  K'(c,k) = (c/4)*96  + (k/6)*24 + (c%4)*6 + (k%6)
-//                      mode 2 (K <= 32 neighbours, c % 8 == 0)  K'(c,k) = (c/8)*192 + (k/3)*24 + (c%8)*3 + (k%3)
+//                      mode 2 (K <= 64 neighbours, c % 8 == 0)  K'(c,k) = (c/8)*192 + (k/3)*24 + (c%8)*3 + (k%3)
 __host__ __device__ __forceinline__ int inter_kperm_inv(int kp, int mode) {  // K' -> c*24 + k
     if (mode == 1) {
         const int blk = kp / 96, r = kp - blk * 96, grp = r / 24, q = r - grp * 24, cl4 = q / 6, i = q - cl4 * 6;
@@ -103,6 +103,10 @@ int launch_inter_group_direct(const float *feats, const int32_t *idx, const Inte
                               long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
                               int ks, cudaStream_t s);
 int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, cudaStream_t s);
+// one input channel (feats NULL = occupancy ones), any row length up to 128: tiles of one K block in plain order
+bool inter_group_occ_ok(int c, int nn, int na, int ks);
+int launch_inter_group_occ(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, long long cols_per_z,
+                           int p_off, int p_cnt, int bc, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
 
 // epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,

@@ -1,7 +1,7 @@
-"""Multi-GPU plumbing: one process per GPU, clouds sharded across ranks, ONE all-reduce of a
-flat fp32 gradient buffer per step (replaces the reference's nn.DataParallel,
-vgtk/vgtk/app/trainer.py:153-160; BatchNorm statistics stay per rank = DataParallel replica
-semantics).  Works with backend "nccl" (NVLink 5 / NVSwitch on the B200 box) and "gloo" (CPU tests).
+"""Multi-GPU plumbing: one process per GPU, clouds sharded across ranks, the gradients of ONE flat fp32 buffer
+all-reduced per step (replaces the reference's nn.DataParallel, vgtk/vgtk/app/trainer.py:153-160; BatchNorm
+statistics stay per rank = DataParallel replica semantics).  Works with backend "nccl" (NVLink 5 / NVSwitch on the
+B200 box) and "gloo" (CPU tests).
 """
 import torch
 import torch.distributed as dist
@@ -22,25 +22,90 @@ def shard_pairs(n_pairs, rank, world_size):
 
 
 class FlatGradSync:
-    """Views every parameter's .grad into one contiguous buffer so that a step needs a single
-    collective (cls backbone: 7.67 M params = 30.7 MB)."""
+    """Views every parameter's .grad into one contiguous buffer (cls network: 7.81 M params = 31.3 MB).
 
-    def __init__(self, params, process_group=None):
+    Plain use: `zero()` ... backward ... `all_reduce_mean()` = ONE collective per step.
+
+    `overlap=True` cuts the buffer into buckets of ~`bucket_bytes` (in parameter order: backward produces the last
+    layers' gradients first) and launches each bucket's all-reduce on a side stream as soon as autograd has
+    accumulated its last gradient (post-accumulate hooks), so the collectives of the head and the deep blocks run
+    under the backward kernels of the shallow ones; `all_reduce_mean()` then only waits for the side stream.
+    The fork/join is plain stream-event ordering, so it can be captured into a CUDA graph together with the backward
+    pass (GraphedTrainStep does).  On CPU tensors (gloo tests) the bucket collectives run synchronously in the hook.
+    """
+
+    def __init__(self, params, process_group=None, overlap=False, bucket_bytes=8 << 20):
         self.params = [p for p in params if p.requires_grad]
         self.group = process_group
         total = sum(p.numel() for p in self.params)
         ref = self.params[0]
         self.flat = torch.zeros(total, dtype=ref.dtype, device=ref.device)
         off = 0
+        self._spans = []
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
+            self._spans.append((off, off + n))
             off += n
-
         self._views = [p.grad for p in self.params]
+        self.overlap = False
+        if overlap:
+            self._setup_overlap(bucket_bytes)
 
+    # ------------------------------------------------------------------ bucketed, overlapped reduction
+    def _distributed(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _setup_overlap(self, bucket_bytes):
+        self.overlap = True
+        per = max(int(bucket_bytes) // self.flat.element_size(), 1)
+        self._buckets, self._bucket_of = [], []   # [lo, hi, n_params], parameter -> bucket
+        lo = cnt = 0
+        for i, (a, b) in enumerate(self._spans):
+            self._bucket_of.append(len(self._buckets))
+            cnt += 1
+            if b - lo >= per or i == len(self._spans) - 1:
+                self._buckets.append([lo, b, cnt])
+                lo, cnt = b, 0
+        self._pending = [b[2] for b in self._buckets]
+        self._side = torch.cuda.Stream(self.flat.device) if self.flat.is_cuda else None
+        self._launched = False
+        for i, p in enumerate(self.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(p):
+            if not self._distributed():
+                return
+            g, v = p.grad, self._views[i]
+            if g is not None and g.data_ptr() != v.data_ptr():   # autograd bound a private gradient: bring it home
+                v.copy_(g)
+                p.grad = v
+            k = self._bucket_of[i]
+            self._pending[k] -= 1
+            if self._pending[k] == 0:
+                self._reduce_bucket(k)
+        return hook
+
+    def _reduce_bucket(self, k):
+        lo, hi, _ = self._buckets[k]
+        chunk = self.flat[lo:hi]
+        ws = dist.get_world_size(self.group)
+        self._launched = True
+        if self._side is None:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.mul_(1.0 / ws)
+            return
+        self._side.wait_stream(torch.cuda.current_stream(self.flat.device))
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group)
+
+    # ------------------------------------------------------------------ public
     def zero(self):
         self.flat.zero_()
+        if self.overlap:
+            self._pending = [b[2] for b in self._buckets]
+            self._launched = False
 
     def rebind(self):
         """Point every parameter's .grad back at its slice of the flat buffer.  `optimizer.zero_grad()` (default
@@ -60,10 +125,17 @@ class FlatGradSync:
         was averaged over) the result is the gradient of the mean over ALL clouds even when the shards are not
         equal (shard_range with a remainder); without it the shards are assumed equal (mean of per-rank means)."""
         self.rebind()
-        if not (dist.is_available() and dist.is_initialized()):
+        if not self._distributed():
             return
         ws = dist.get_world_size(self.group)
-        if ws == 1:
+        if self.overlap and local_units is None:
+            # buckets whose gradients all arrived are already reduced (or in flight on the side stream); a bucket
+            # with a parameter that received no gradient this step is reduced here
+            for k, left in enumerate(self._pending):
+                if left > 0:
+                    self._reduce_bucket(k)
+            if self._side is not None:
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
             return
         if local_units is None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
@@ -76,25 +148,46 @@ class FlatGradSync:
         self.flat.div_(n)
 
 
-class GraphedTrainStep:
-    """One training step (zero grads, forward, loss, backward) captured ONCE into a CUDA graph and replayed.
+def _tree_map(fn, obj):
+    if isinstance(obj, torch.Tensor):
+        return fn(obj)
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_tree_map(fn, o) for o in obj)
+    return obj
 
-    The SPConv stack issues ~3000 small-to-medium kernel launches per step; replayed from a graph the GPU never
-    waits for the host, which matters whenever the caller synchronises every step (reads the loss, feeds
-    fresh host data).  The gradient all-reduce (if a process group is up) and the optimizer step run eagerly
-    after the replay, so any torch optimizer works unchanged.
+
+def _tree_copy(dst, src):
+    if isinstance(dst, torch.Tensor):
+        if src is not None and src.data_ptr() != dst.data_ptr():
+            dst.copy_(src, non_blocking=True)
+    elif isinstance(dst, (tuple, list)):
+        for d, s in zip(dst, src):
+            _tree_copy(d, s)
+
+
+class GraphedTrainStep:
+    """One training step (zero grads, forward, loss, backward, and -- with an overlapping FlatGradSync -- the
+    bucketed gradient all-reduce) captured ONCE into a CUDA graph and replayed.
+
+    The SPConv stack issues several hundred small-to-medium kernel launches per step; replayed from a graph the
+    GPU never waits for the host, which matters whenever the caller synchronises every step (reads the loss, feeds
+    fresh host data) and when the per-GPU batch is small (strong scaling).  The optimizer step runs eagerly after
+    the replay, so any torch optimizer works unchanged.
 
         step = GraphedTrainStep(model, loss_fn, optimizer, sync, x_example, labels_example)
         loss = step(x, labels)            # x / labels: CUDA or pinned-host tensors of the captured shapes
 
-    `loss_fn(model_output, labels) -> scalar tensor`; `sync` is a FlatGradSync (gradients live in its flat
-    buffer, zeroed inside the graph).  Shapes, dtypes and the module's training mode are frozen at capture.
+    `loss_fn(model_output, labels) -> scalar tensor`; `labels` is a tensor or a tuple of tensors; `sync` is a
+    FlatGradSync (gradients live in its flat buffer, zeroed inside the graph).  Shapes, dtypes and the module's
+    training mode are frozen at capture.
     """
 
     def __init__(self, model, loss_fn, optimizer, sync, x_example, labels_example, warmup=3):
         self.model, self.loss_fn, self.optimizer, self.sync = model, loss_fn, optimizer, sync
         self.x = x_example.detach().clone()
-        self.labels = labels_example.detach().clone()
+        self.labels = _tree_map(lambda t: t.detach().clone(), labels_example)
+        # the collectives are captured with the backward pass only when they were launched from its hooks
+        self.reduce_in_graph = bool(getattr(sync, "overlap", False)) and sync._distributed() and sync.flat.is_cuda
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -125,14 +218,17 @@ class GraphedTrainStep:
         self.sync.zero()
         loss = self.loss_fn(self.model(self.x), self.labels)
         loss.backward()
+        if self.reduce_in_graph:
+            self.sync.all_reduce_mean()   # joins the side stream the bucket collectives were forked onto
         return loss.detach()
 
     def __call__(self, x=None, labels=None):
         if x is not None and x.data_ptr() != self.x.data_ptr():
             self.x.copy_(x, non_blocking=True)
-        if labels is not None and labels.data_ptr() != self.labels.data_ptr():
-            self.labels.copy_(labels, non_blocking=True)
+        if labels is not None:
+            _tree_copy(self.labels, labels)
         self.graph.replay()
-        self.sync.all_reduce_mean()
+        if not self.reduce_in_graph:
+            self.sync.all_reduce_mean()
         self.optimizer.step()
         return self.loss

@@ -1,10 +1,16 @@
-"""Stub-import harness that runs the UNMODIFIED reference Python on CPU.
+"""Stub-import harness that runs the UNMODIFIED reference Python (on CPU, or on the GPU with the
+reference's own CUDA extensions from oracle/_ref).
 
 TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Used in the build container
 (where /root/reference is mounted) by oracle/make_golden.py and
-oracle/make_constants.py to pin the oracle and to generate tests/golden/*.
-Nothing under tests -m gpu, smoke() or bench.py imports this module:
-/root/reference does not exist on the GPU box.
+oracle/make_constants.py to pin the oracle and to generate tests/golden/*, and by
+bench.py's reference arms (`--impl reference`, `cpu_baseline`, `reference_gpu`) -- the
+only places that may execute anything under oracle/.  On the GPU box /root/reference
+does not exist: there the harness reads the reference's Python from baseline/_ref/, a
+git-ignored verbatim copy made in the build container by oracle/vendor_ref.py (the
+reference is a Python package with an unbuildable setup.py -- it compiles its CUDA
+extensions at install time -- so the copy stands in for `pip install --target
+baseline/_ref`).  Nothing from the reference is committed to the repository.
 
 What is stubbed:
   * trimesh (==3.2.0 upstream, not installed): `load()` returns an object with
@@ -27,7 +33,23 @@ import types
 import numpy as np
 import torch
 
-REFERENCE_ROOT = os.environ.get("EPN_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, "baseline", "_ref")
+
+
+def _find_root():
+    for cand in (os.environ.get("EPN_REFERENCE_ROOT"), "/root/reference", VENDORED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "vgtk", "vgtk")) and os.path.isdir(os.path.join(cand, "SPConvNets")):
+            return cand
+    return os.environ.get("EPN_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find_root()
+
+
+def available():
+    """True when the reference's Python tree can be imported (build container, or baseline/_ref on the GPU box)."""
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "vgtk", "vgtk"))
 
 
 # ----------------------------------------------------------------- PLY readers
@@ -112,8 +134,27 @@ def _make_plyfile():
 
 
 def _make_cuda_stubs():
-    """vgtk.cuda.* served by the C oracle (CPU tensors in, CPU tensors out)."""
+    """vgtk.cuda.* : CPU tensors are served by the C oracle; CUDA tensors by the REFERENCE's own CUDA
+    extensions compiled into oracle/_ref (oracle/build_ref.py) -- never by this repository's library."""
     from oracle import epn_oracle as O
+    from oracle import build_ref
+
+    ref_ext = {}
+
+    def ext(name):
+        if name not in ref_ext:
+            ref_ext[name] = build_ref.load_ref(name)
+            if ref_ext[name] is None:
+                raise RuntimeError("oracle/_ref/vgtk_ref_%s.so not built (python -m oracle.build_ref)" % name)
+        return ref_ext[name]
+
+    def dual(ext_name, fn_name, cpu_fn):
+        def call(*a):
+            if any(isinstance(t, torch.Tensor) and t.is_cuda for t in a):
+                with torch.cuda.device(next(t.device for t in a if isinstance(t, torch.Tensor) and t.is_cuda)):
+                    return getattr(ext(ext_name), fn_name)(*a)
+            return cpu_fn(*a)
+        return call
 
     pkg = types.ModuleType("vgtk.cuda")
     pkg.__path__ = []
@@ -121,14 +162,14 @@ def _make_cuda_stubs():
     gathering = types.ModuleType("vgtk.cuda.gathering")
     zpconv = types.ModuleType("vgtk.cuda.zpconv")
 
-    grouping.ball_query = lambda new_xyz, xyz, radius, nsample: O.ball_query(new_xyz, xyz, radius, nsample)
-    grouping.furthest_point_sampling = lambda xyz, m: O.furthest_point_sampling(xyz, m)
-    gathering.gather_points_forward = lambda pts, idx: O.gather_points_forward(pts, idx)
-    gathering.gather_points_backward = lambda g, idx, n: O.gather_points_backward(g, idx, n)
-    zpconv.inter_zpconv_forward = O.zp_inter_forward
-    zpconv.inter_zpconv_backward = O.zp_inter_backward
-    zpconv.intra_zpconv_forward = O.zp_intra_forward
-    zpconv.intra_zpconv_backward = O.zp_intra_backward
+    grouping.ball_query = dual("grouping", "ball_query", lambda new_xyz, xyz, radius, nsample: O.ball_query(new_xyz, xyz, radius, nsample))
+    grouping.furthest_point_sampling = dual("grouping", "furthest_point_sampling", lambda xyz, m: O.furthest_point_sampling(xyz, m))
+    gathering.gather_points_forward = dual("gathering", "gather_points_forward", lambda pts, idx: O.gather_points_forward(pts, idx))
+    gathering.gather_points_backward = dual("gathering", "gather_points_backward", lambda g, idx, n: O.gather_points_backward(g, idx, n))
+    zpconv.inter_zpconv_forward = dual("zpconv", "inter_zpconv_forward", O.zp_inter_forward)
+    zpconv.inter_zpconv_backward = dual("zpconv", "inter_zpconv_backward", O.zp_inter_backward)
+    zpconv.intra_zpconv_forward = dual("zpconv", "intra_zpconv_forward", O.zp_intra_forward)
+    zpconv.intra_zpconv_backward = dual("zpconv", "intra_zpconv_backward", O.zp_intra_backward)
     pkg.grouping, pkg.gathering, pkg.zpconv = grouping, gathering, zpconv
     return {"vgtk.cuda": pkg, "vgtk.cuda.grouping": grouping,
             "vgtk.cuda.gathering": gathering, "vgtk.cuda.zpconv": zpconv}
@@ -165,8 +206,9 @@ def load_reference():
     return vgtk
 
 
-def load_spconvnets():
-    """Import SPConvNets.utils.base_so3conv + the three model builders."""
+def load_spconvnets(gpu_ops=None):
+    """Import SPConvNets.utils.base_so3conv + the three model builders.  (`gpu_ops` is informational: the
+    vgtk.cuda stubs pick the reference's CUDA extensions or the C oracle per call from the tensors' device.)"""
     load_reference()
     if "M" in _loaded:
         return _loaded["M"]
@@ -177,3 +219,24 @@ def load_spconvnets():
         sys.argv = argv
     _loaded["M"] = M
     return M
+
+
+def cls_opt(input_num=1024, kanchor=60, device="cpu"):
+    """The slice of the reference's `opt` namespace its build_model functions read
+    (SPConvNets/options.py:9-103, SPConvNets/models/cls_so3net_pn.py:58-66)."""
+    o = types.SimpleNamespace()
+    o.device = device
+    o.model = types.SimpleNamespace(input_num=input_num, dropout_rate=0.0, kpconv=False, kanchor=kanchor, flag="max",
+                                    search_radius=0.4, representation="quat")
+    o.train_loss = types.SimpleNamespace(temperature=3.0)
+    return o
+
+
+def build_cls_model(input_num=1024, kanchor=60):
+    """The reference's classification network, built by ITS build_model (default init, caller seeds)."""
+    import contextlib
+    import io
+    load_spconvnets()
+    mod = importlib.import_module("SPConvNets.models.cls_so3net_pn")
+    with contextlib.redirect_stdout(io.StringIO()):
+        return mod.build_model(cls_opt(input_num, kanchor))

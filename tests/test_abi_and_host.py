@@ -122,6 +122,25 @@ ref.zero_grad()
 ref(x[:7]).pow(2).sum(1).mean().backward()
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p.grad, q.grad, rtol=1e-5, atol=1e-6), (p.grad, q.grad)
+# bucketed reduction launched from the post-accumulate hooks (overlap=True; synchronous on CPU tensors):
+# 4 parameters in 3 buckets, one of them left without a gradient in the second step
+model2 = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Linear(5, 3))
+model2.load_state_dict(ref.state_dict())
+sync2 = FlatGradSync(model2.parameters(), overlap=True, bucket_bytes=64)
+assert len(sync2._buckets) >= 2
+lo, hi = shard_range(8, dist.get_rank(), 2)
+for frozen in (False, True):
+    sync2.zero()
+    h = model2[0](x[lo:hi])
+    out = model2[1](h.detach() if frozen else h)   # frozen: layer 0 receives no gradient this step
+    out.pow(2).sum().backward()
+    sync2.all_reduce_mean()
+    ref.zero_grad()
+    hr = ref[0](x)
+    (ref[1](hr.detach() if frozen else hr).pow(2).sum() / 2).backward()
+    for p, q in zip(model2.parameters(), ref.parameters()):
+        want = torch.zeros_like(p) if q.grad is None else q.grad
+        assert torch.allclose(p.grad, want, rtol=1e-5, atol=1e-6), (frozen, p.grad, want)
 dist.destroy_process_group()
 print("ok")
 """

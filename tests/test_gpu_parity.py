@@ -585,15 +585,19 @@ def test_dw_from_kept_forward_tiles_equals_recomputed(E, kind, c_in, c_out, p, n
 
 
 # ------------------------------ shapes of the other BASELINE configs (rotation model, 3DMatch model, sweep)
-@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,radius,sigma,kanchor", [
-    (32, 32, 512, 1, 32, 0.2828, 0.04, 60),      # reg model b0l1 (K=32)
-    (32, 64, 512, 2, 64, 0.4, 0.08, 60),         # reg model b1l0 (K=64 -> generic grouping path)
-    (1, 32, 2048, 4, 128, 0.08, 0.0032, 60),     # inv model layer 0 (2048 pts, stride 4, K=128, FPS)
-    (32, 32, 512, 1, 32, 0.113, 0.0128, 60),     # inv model layer 1
-    (16, 16, 256, 1, 32, 0.7, 0.25, 12),         # sweep: A=12 (first 12 anchors, inter conv only)
-    (8, 8, 256, 1, 16, 0.5, 0.125, 20),          # config 1 anchor count with real features
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,radius,sigma,kanchor,geom", [
+    (32, 32, 512, 1, 32, 0.2828, 0.04, 60, "surface"),      # reg model b0l1 (K=32)
+    (32, 64, 512, 2, 64, 0.4, 0.08, 60, "surface"),         # reg model b1l0 (K=64, ~20 distinct: 32-neighbour kernel)
+    (128, 256, 128, 2, 64, 0.8, 0.32, 60, "surface"),       # reg model b3l0 (K=64)
+    (1, 32, 2048, 4, 128, 0.08, 0.0032, 60, "ball"),        # inv model layer 0 (2048 pts, stride 4, K=128, FPS)
+    (32, 32, 512, 1, 32, 0.113, 0.0128, 60, "ball"),        # inv model layer 1
+    (32, 64, 512, 2, 64, 0.16, 0.0256, 60, "ball"),         # inv model b1l0: ~33 distinct of K=64 (both kernels run)
+    (64, 128, 256, 2, 64, 0.226, 0.0512, 60, "ball"),       # inv model b2l0: ~46 distinct
+    (128, 128, 128, 2, 64, 0.32, 0.1024, 60, "ball"),       # inv model b3l0: up to 64 distinct
+    (16, 16, 256, 1, 32, 0.7, 0.25, 12, "surface"),         # sweep: A=12 (first 12 anchors, inter conv only)
+    (8, 8, 256, 1, 16, 0.5, 0.125, 20, "surface"),          # config 1 anchor count with real features
 ])
-def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, radius, sigma, kanchor):
+def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, radius, sigma, kanchor, geom):
     """Forward + gradients of one InterSO3Conv against the CPU oracle port (reference op chain) on one cloud."""
     from oracle import torch_port as TP
     torch.manual_seed(1)
@@ -602,9 +606,8 @@ def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, r
         from epn_pointcloud_b200 import functional as L
         anchors = L.get_anchors(kanchor) if kanchor in (1, 20, 40) else L.get_anchors(60)[:kanchor]
         conv.anchors = torch.from_numpy(anchors.copy()).to(DEV)
-    surface = c_in != 1 or p_in <= 1024
-    xyz = sphere(1, p_in, 31 + p_in, surface=surface)
-    if p_in == 2048:
+    xyz = sphere(1, p_in, 31 + p_in, surface=(geom == "surface"))
+    if geom == "ball":
         xyz = xyz * 0.4   # 3DMatch patches live in a ball of radius 0.4 (search_radius)
     feats = torch.randn(1, c_in, p_in, kanchor, generator=torch.Generator().manual_seed(7))
     if c_in == 1:
