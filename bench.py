@@ -112,8 +112,7 @@ class Workload:
             self.model_cls = heads.RegSO3ConvModel
             self.desc = ("ModelNet40 relative-rotation network (7+7 SPConv layers, K=64/32, pair head) fwd+bwd+Adam, "
                          "32 pairs = 64 clouds of 1024 pts, 60 anchors (BASELINE configs[2])")
-            from epn_pointcloud_b200 import functional as L
-            self._metric = losses.MultiTaskDetectionLoss(torch.from_numpy(L.get_anchors(60)), nr=4)
+            self._metric = None   # built on the device in build()
             self.loss = lambda out, lab: self._metric(out[0], lab[0], out[1], lab[1], lab[2])[0]
         elif name == "inv":
             self.n_points, self.global_items, self.units_per_item = 2048, 8, 2
@@ -126,8 +125,9 @@ class Workload:
                 d = out[0]
                 n = d.shape[0] // 2
                 dist_ = losses.pairwise_distance_matrix(d[:n], d[n:])
-                pos, neg = torch.diagonal(dist_), losses.batch_hard_negative_mining(dist_)
-                return torch.nn.functional.softplus(pos - neg, beta=1.0).mean()   # TripletBatchLoss, 'soft'
+                # batch-hard mining without boolean indexing (no host sync: the step is captured into a CUDA graph)
+                neg = (dist_ + torch.eye(n, device=d.device, dtype=d.dtype) * 1e9).min(1)[0]
+                return torch.nn.functional.softplus(torch.diagonal(dist_) - neg, beta=1.0).mean()   # TripletBatchLoss, 'soft'
             self.loss = triplet
         else:
             raise ValueError(name)
@@ -136,7 +136,8 @@ class Workload:
         torch.manual_seed(0)  # identical weights on every rank
         m = self.model_cls(self.params).to(dev).train()
         if self.name == "reg":
-            self._metric = self._metric.to(dev)
+            from epn_pointcloud_b200 import functional as L, losses
+            self._metric = losses.MultiTaskDetectionLoss(torch.from_numpy(L.get_anchors(60)).to(dev), nr=4)
         return m
 
     def batch(self, n_items, seed):
@@ -366,8 +367,13 @@ class Runner:
 
         step, graphed = eager_step, None
         if graph:
-            graphed = GraphedTrainStep(model, wl.loss, opt, sync, x_dev, labels, warmup=warmup)
-            step = lambda x: graphed(x)  # noqa: E731
+            try:
+                graphed = GraphedTrainStep(model, wl.loss, opt, sync, x_dev, labels, warmup=warmup)
+                step = lambda x: graphed(x)  # noqa: E731
+            except Exception as e:  # a loss with a host sync (SVD of the rotation loss) cannot be captured: run eagerly
+                torch.cuda.synchronize()
+                self.graph_fallback = repr(e)[:160]
+                graphed = None
         for _ in range(warmup):
             step(x_dev)
         return {"step": step, "eager_step": eager_step, "x_host": x_host, "x_dev": x_dev,
@@ -385,6 +391,7 @@ class Runner:
         if S["graphed"] is not None:  # replayed launches are not seen by the host-side counter: counted once at capture
             launches = S["graphed"].launches_per_replay * steps
         res = {"value": units * steps / (ms * 1e-3), "ms_per_step": ms / steps, "launches": int(launches),
+               "launch": "CUDA graph replay" if S["graphed"] is not None else "eager",
                "clocks": clocks.summary(), "units_per_gpu": items_per_rank * wl.units_per_item, "setup": S}
         if e2e:
             x_host, x_stage = S["x_host"], S["x_stage"]
@@ -578,7 +585,7 @@ def main():
                 f_ms = R.measure_forward(S2["model"], S2["x_dev"], 3, 1)
                 other[name] = {"workload": w2.desc, "value": r["value"], "unit": "clouds/s", "ms_per_step": r["ms_per_step"],
                                "scaling": "strong", "clouds_per_gpu": r["units_per_gpu"], "global_batch": r["units_per_gpu"] * world,
-                               "gpu_launches_per_step": r["launches"] // max(args.steps // 2, 3),
+                               "gpu_launches_per_step": r["launches"] // max(args.steps // 2, 3), "launch": r["launch"],
                                "forward_clouds_per_s": world * r["units_per_gpu"] / (f_ms * 1e-3), "forward_ms": f_ms}
                 del S2, r
             except Exception as e:  # a failure here must not lose the headline line

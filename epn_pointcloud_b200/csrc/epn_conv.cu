@@ -34,10 +34,10 @@ static int gemm_backend() {
 
 static std::atomic<int> g_fused{-1};
 
-static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused inter-conv kernel instead of grouping + GEMM
+static int fused_enabled() {  // default ON; EPN_FUSED=0 / epn_set_fused_inter(0): grouping kernel + GEMM kernel instead
     int v = g_fused.load();
     if (v < 0) {
-        v = (getenv("EPN_FUSED") && strcmp(getenv("EPN_FUSED"), "1") == 0) ? 1 : 0;
+        v = (getenv("EPN_FUSED") && strcmp(getenv("EPN_FUSED"), "0") == 0) ? 0 : 1;
         g_fused.store(v);
     }
     return v;
@@ -46,7 +46,7 @@ static int fused_enabled() {  // EPN_FUSED=1 / epn_set_fused_inter(1): one fused
 // Inter grouping with the bf16 split in registers + permuted K order (epn_group_direct.cu): 0 or the K' mode the
 // forward will use for this call (the backward is told through the grouped_layout word, never re-derives it).
 static int inter_direct(const float *feats, int c_in, int nn, int na, int ks) {
-    if (gemm_backend() != 0 || fused_enabled() || c_in == 1) return 0;
+    if (gemm_backend() != 0 || c_in == 1) return 0;
     return inter_group_direct_mode(feats, c_in, nn, na, ks);
 }
 
@@ -409,21 +409,24 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     if (grouped != nullptr) EPN_CHECK_GROUPED(epn_inter_so3conv_grouped_bytes(b, c_in, p, nn, na, ks));
     uint8_t *keep = static_cast<uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
-    const int kperm = inter_direct(feats, c_in, nn, na, ks);
+    // fused route: ONE kernel over every cloud, G stays in shared memory (its K' mode numbers are the direct kernels')
+    int fused = 0;
+    if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && c_in > 1 && sp.pc == p)
+        fused = inter_fused_mode(c_in, c_out, p, nn, na, ks, grouped != nullptr);
+    const int kperm = fused ? fused : inter_direct(feats, c_in, nn, na, ks);
     if (grouped != nullptr) {
         EPN_REQUIRE_PTR(grouped_layout);
         *grouped_layout = encode_layout(kperm, sp);
     }
     EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm));
-    if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && sp.pc == p && inter_fused_ok(c_in, c_out, p, nn, na, ks)) {
-        // one launch over every cloud: G stays in shared memory; kept tiles (training) keep the slab layout the
-        // weight-gradient pass expects
+    if (fused) {
+        // kept tiles (training) keep the slab layout the weight-gradient pass expects
         InterGeom g{xyz, centers, anchors, kernels, sigma};
         const long long cols = (long long)p * na;
         const int rc = launch_inter_fused(feats, idx, g, ws.tilesW, out, (long long)c_out * p * na, (long long)p * na, keep,
                                           cdiv(ck, 32), cols, sp.bc, split_tiles_bytes((long long)sp.bc * cols, ck, 128), 0, p,
                                           b, c_in, c_out, p_in, p, nn, na, ks, s);
-        if (rc != 1) return rc;
+        return rc == 1 ? EPN_ERR_SHAPE : rc;
     }
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;

@@ -6,16 +6,26 @@
 //    -> so3conv/modules.py:48-55)
 //
 // A CTA owns PTS consecutive output points of one cloud (PTS*64 rows of the MMA M dimension, row = pt*64 + anchor,
-// anchors 60..63 of a point are dead rows).  Producer warps (PTS*64*(24/KG) threads, same mapping as
-// inter_group_tiles_kernel: lane <-> anchor, warp pair <-> group of KG kernel points, kernel weights in
-// registers as fp32x2 pairs) stream the input channels in chunks of CCH: bulk-copy gather of the neighbours'
-// feature rows -> per-anchor spatial contraction (fp32 SIMT) -> fp32 staging -> bf16 hi/lo split written as
-// canonical K-major UMMA operand tiles into shared memory.  One control thread streams the weight tiles
-// (bf16 hi/lo, rows = c_out) from L2 through a ring of 16-k stages with bulk copies and issues three
-// tcgen05.mma (hi*hi, hi*lo, lo*hi) per 16-wide k step into a [128 x c_out] fp32 accumulator in TMEM while the
-// producers work on the next chunk.  The epilogue (all producer warps) reads TMEM and stores out[z,o,p,.] rows
-// (128 contiguous bytes per warp and output channel).  In training the conversion pass also writes the operand
-// tiles to global memory (what the weight-gradient GEMM consumes, see epn_gemm_dw.cu).
+// anchors 60..63 of a point are dead rows).  512 threads = 480 producers + one control warp: 16 warps is what lets
+// every thread have 128 registers (4 warps per SM sub-partition; a 17th warp would cap the kernel at 96 and spill
+// the weights), so the producers are packed 60 anchors per kernel-point group with no dead lanes.
+// The PRODUCERS are the in-register-split grouping kernels of
+// epn_group_direct.cu (thread <-> (anchor, group of KG kernel points), kernel weights in registers as
+// fp32x2 pairs, bulk-copy gather of the distinct neighbours' feature rows, FFMA2 contraction, bf16 hi/lo split as the
+// values leave the FMA loop) -- but their 16-byte operand pieces go to a double-buffered A tile in SHARED memory
+// (canonical K-major UMMA layout, K in the permuted order K'(c,k) of epn_internal.cuh) instead of global memory.
+// One control warp streams the weight tiles (bf16 hi/lo, rows = c_out, same K' order) from L2 through a ring of
+// 16-k stages with bulk copies and issues three tcgen05.mma (hi*hi, hi*lo, lo*hi) per 16-wide k step into a
+// [128 x c_out] fp32 accumulator in TMEM, one "granule" (4 or 8 channels) behind the producers.  The epilogue (all
+// producer warps) reads TMEM and stores out[z,o,p,.] rows (128 contiguous bytes per warp and output channel).
+//   MODE 1: rows of <= 16 slots, 6 kernel points per thread, TWO points per CTA, granule = 4 channels (96 K').
+//   MODE 2: up to 32 distinct neighbours per pass, 3 kernel points per thread, ONE point per CTA (rows 64..127 of
+//           the MMA are dead), granule = 8 channels (192 K').  A point with more distinct neighbours (rows of up to
+//           128 slots: the K = 64 layers of the rotation / 3DMatch models) simply runs further passes over the next
+//           32 neighbours, accumulating into the same TMEM tile (the GEMM is linear in G).
+// In training the producers also write their pieces to global memory (the operand tiles the weight-gradient GEMM
+// consumes, epn_gemm_dw.cu); that needs the complete G of a point in one pass, i.e. rows of <= 32 slots.
+#include "epn_dedup.cuh"
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
@@ -24,18 +34,24 @@ using namespace umma;
 
 namespace {
 
-constexpr int FU_LANES = 64;  // anchor lanes per kernel-point group
+constexpr int FU_LANES = 60;  // anchors per kernel-point group: no dead lanes (see the header comment)
 constexpr int FU_KS = 24;     // kernel points (kpsphere24)
 constexpr int FU_NA = 60;
+constexpr int FU_CCH = 4;     // channels per gather chunk
+constexpr int FU_CTRL = 32;   // control warp
+
+template <int MODE> struct FuCfg;
+template <> struct FuCfg<1> { static constexpr int NN = 16, KG = 6, PTS = 2, GCH = 4, CAP = 16; };
+template <> struct FuCfg<2> { static constexpr int NN = 32, KG = 3, PTS = 1, GCH = 8, CAP = DEDUP_MAX_RAW; };
 
 struct FusedParams {
-    const float *feats;      // [b, c, p_in, 60] or null (occupancy features == 1, c == 1)
+    const float *feats;      // [b, c, p_in, 60]
     const int32_t *idx;      // [b, p, nn]
     InterGeom g;
-    const uint8_t *Wt;       // weight tiles [k_blocks] of trb rows (split tiles, rows = c_out, K = c*24)
+    const uint8_t *Wt;       // weight tiles [k_blocks] of trb rows (split tiles, rows = c_out, K = K'(c,k))
     float *out;              // out + z*out_sz + o*out_so + pl*60 + a
     long long out_sz, out_so;
-    uint8_t *keep;           // optional: forward operand tiles in global memory (rows = (z,pl,a), K = (c,k))
+    uint8_t *keep;           // optional: forward operand tiles in global memory (rows = (z,pl,a), K = K'(c,k))
     int keep_k_blocks, keep_slab_clouds;   // clouds z are stored in slabs of keep_slab_clouds, each slab a tile matrix
     long long keep_cols_per_z;
     size_t keep_slab_bytes;
@@ -46,44 +62,49 @@ struct FusedParams {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
-template <int NN, int KG, int CCH, int PTS, bool HAS_FEATS>
-__global__ void __launch_bounds__(PTS *FU_LANES *(FU_KS / KG) + 128, 1)
+template <int MODE>
+__global__ void __launch_bounds__(FuCfg<MODE>::PTS *FU_LANES *(FU_KS / FuCfg<MODE>::KG) + FU_CTRL, 1)  // 480 + 32
 inter_fused_kernel(FusedParams P) {
-    constexpr int NA = FU_NA;
+    using C = FuCfg<MODE>;
+    constexpr int NN = C::NN, KG = C::KG, PTS = C::PTS, GCH = C::GCH, NA = FU_NA, CCH = FU_CCH;
     constexpr int GROUPS = FU_KS / KG;
     constexpr int PT_THR = FU_LANES * GROUPS;     // producer threads per point
-    constexpr int NPROD = PTS * PT_THR;           // producer threads
-    constexpr int GSTR = NA + 1;
-    constexpr int CKK = CCH * FU_KS;              // (c,k) rows per chunk
-    constexpr int KBC = CKK / 32;                 // k-blocks per chunk
-    static_assert(CKK % 32 == 0, "chunk must be whole k-blocks");
-    constexpr int ROWS = PTS * 64;                // valid rows of the A tiles
+    constexpr int NPROD = PTS * PT_THR;           // producer threads (480 in both modes)
+    constexpr int NPWARPS = NPROD / 32;           // 15
+    constexpr int NWARPS = NPWARPS + 1;
+    static_assert(NPROD == 480, "15 producer warps + the control warp");
+    constexpr int GK = GCH * FU_KS;               // K' values per granule
+    constexpr int KBG = GK / 32;                  // k-blocks per granule
+    constexpr int STEPS_G = KBG * 2;              // 16-k steps per granule
+    constexpr int CH_G = GCH / CCH;               // gather chunks per granule
+    constexpr int ROWS = PTS * 64;                // rows of the A tiles that exist in shared memory
     constexpr uint32_t A_LBO = ROWS * 16;         // bytes between 8-wide k chunks
     constexpr uint32_t A_PART = 4 * A_LBO;        // hi (or lo) part of one k-block
     constexpr uint32_t A_KB = 2 * A_PART;         // one k-block
-    constexpr uint32_t A_BYTES = KBC * A_KB + (PTS == 1 ? 1024 : 0);  // PTS == 1: the M=128 MMA over-reads 64 dead rows
+    constexpr uint32_t A_BUF = KBG * A_KB;        // one granule
+    constexpr uint32_t A_BYTES = 2 * A_BUF + (PTS == 1 ? 1024 : 0);  // PTS == 1: the M=128 MMA over-reads 64 dead rows
+    constexpr uint32_t ROW_BYTES = NA * 4;
 
     extern __shared__ __align__(128) uint8_t smem[];
-    // carve-up (all offsets multiples of 128 bytes)
-    uint8_t *a_tiles = smem;
+    uint8_t *a_tiles = smem;                                               // [2][KBG] k-blocks
     float *Fs = reinterpret_cast<float *>(smem + A_BYTES);                 // [PTS][2][CCH][NN][NA]
-    float *Gs = Fs + PTS * 2 * CCH * NN * NA;                               // [PTS][CKK][GSTR]
-    float *hdr = Gs + PTS * CKK * GSTR;                                     // [PTS][NN*6]
-    uint8_t *ring = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(hdr + PTS * NN * 6) + 127) & ~(uintptr_t)127);
+    uint8_t *ring = reinterpret_cast<uint8_t *>(Fs + PTS * 2 * CCH * NN * NA);  // weight ring, nst stages
+    __shared__ NeighbourList<C::CAP> s_L[PTS];
     __shared__ __align__(8) uint64_t s_gbar[PTS][2];   // gather buffers
     __shared__ __align__(8) uint64_t s_wfull[8], s_wempty[8];
-    __shared__ __align__(8) uint64_t s_afull, s_afree, s_accum;
+    __shared__ __align__(8) uint64_t s_afull[2], s_afree[2], s_accum;
     __shared__ uint32_t s_tmem;
-    __shared__ int s_nu[PTS];
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    const int warp = tid >> 5, lane = tid & 31;
     const bool is_ctrl = tid >= NPROD;
     const int z = blockIdx.y;
     const uint32_t stage_bytes = (uint32_t)P.trb * 64u;  // 16 k of hi + 16 k of lo
-    const int nchunks = P.c / CCH;
-    const int total_steps = nchunks * KBC * 2;
+    const int ngran = P.c / GCH;                          // granules per pass
 
     if (tid == 0) {
         for (int i = 0; i < PTS; ++i) {
@@ -94,30 +115,48 @@ inter_fused_kernel(FusedParams P) {
             mbar_init(smem_u32(&s_wfull[i]), 1);
             mbar_init(smem_u32(&s_wempty[i]), 1);
         }
-        mbar_init(smem_u32(&s_afull), 1);
-        mbar_init(smem_u32(&s_afree), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&s_afull[i]), NPWARPS);   // one arrival per producer warp
+            mbar_init(smem_u32(&s_afree[i]), 1);
+        }
         mbar_init(smem_u32(&s_accum), 1);
         fence_barrier_init();
     }
-    if (warp == NPROD / 32) tmem_alloc(smem_u32(&s_tmem), P.tmem_cols);
+    if (warp == NPWARPS) tmem_alloc(smem_u32(&s_tmem), P.tmem_cols);
+
+    // ---- distinct neighbours of the PTS points: DW whole warps per point do the work, every thread of the CTA takes
+    //      part in the three barriers of dedup_row
+    {
+        constexpr int DW = MODE == 1 ? 1 : 4;                      // warps per point (rows of <= 16 / <= 128 slots)
+        const bool worker = tid < PTS * DW * 32;
+        const int dpt = worker ? tid / (DW * 32) : 0;
+        const int dpi = P.p_off + blockIdx.x * PTS + dpt;
+        dedup_row(s_L[dpt], P.idx + ((size_t)z * P.p + dpi) * P.nn, worker ? P.nn : 0, P.g.xyz + (size_t)z * 3 * P.p_in,
+                  P.g.centers + (size_t)z * 3 * P.p, P.p_in, P.p, dpi, worker ? tid - dpt * DW * 32 : (1 << 20),
+                  worker ? DW * 32 : 1, [] { __syncthreads(); });
+    }
+    const int pt = is_ctrl ? 0 : tid / PT_THR;
+    const int ptid = tid - pt * PT_THR;
+    const int pl = blockIdx.x * PTS + pt;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
+    // passes over the distinct neighbours (MODE 1: always one; MODE 2: ceil(distinct / 32), CTA-uniform as PTS == 1)
+    const int npass = MODE == 1 ? 1 : max(1, (s_L[0].total + NN - 1) / NN);
+    const int total_gran = npass * ngran;
 
     if (is_ctrl) {
-        // ------------------------------------------------------------ control warp: W ring + MMA issue
-        // a whole warpgroup (setmaxnreg is a warpgroup-wide instruction) of which one thread works: it hands its
-        // registers to the producers
-        // (setmaxnreg rebalancing faulted on the B200 in this configuration; the kernel runs at 96 registers)
+        // ------------------------------------------------------------ control warp: W ring + MMA issue (one thread)
         if (tid == NPROD) {
+            const int total_steps = total_gran * STEPS_G, steps_pass = ngran * STEPS_G;
             const uint32_t ring_u32 = smem_u32(ring);
             const uint32_t half_bytes = (uint32_t)P.trb * 32u;
             const size_t w_tile = tile_bytes(P.trb), w_part = part_bytes(P.trb);
-            auto load_w = [&](int j) {  // 16-k step j -> ring slot j % nst
-                const int slot = j % P.nst;
+            auto load_w = [&](int j) {  // 16-k step j -> ring slot j % nst (every pass re-streams W)
+                const int slot = j % P.nst, jw = j % steps_pass;
                 const uint32_t bar = smem_u32(&s_wfull[slot]);
-                const uint8_t *src = P.Wt + (size_t)(j >> 1) * w_tile + (size_t)(j & 1) * half_bytes;
+                const uint8_t *src = P.Wt + (size_t)(jw >> 1) * w_tile + (size_t)(jw & 1) * half_bytes;
                 mbar_arrive_expect_tx(bar, stage_bytes);
                 bulk_g2s(ring_u32 + slot * stage_bytes, src, half_bytes, bar);
                 bulk_g2s(ring_u32 + slot * stage_bytes + half_bytes, src + w_part, half_bytes, bar);
@@ -127,14 +166,15 @@ inter_fused_kernel(FusedParams P) {
             const uint32_t b_lbo = (uint32_t)P.trb * 16u;
             const uint32_t a_u32 = smem_u32(a_tiles);
             int j = 0;
-            for (int chunk = 0; chunk < nchunks; ++chunk) {
-                mbar_wait(smem_u32(&s_afull), (uint32_t)chunk & 1u);
+            for (int gi = 0; gi < total_gran; ++gi) {
+                const int ab = gi & 1;
+                mbar_wait(smem_u32(&s_afull[ab]), (uint32_t)(gi >> 1) & 1u);
                 tc_fence_after();
-                for (int s = 0; s < KBC * 2; ++s, ++j) {
+                for (int s = 0; s < STEPS_G; ++s, ++j) {
                     const int slot = j % P.nst;
                     mbar_wait(smem_u32(&s_wfull[slot]), (uint32_t)(j / P.nst) & 1u);
                     tc_fence_after();
-                    const uint32_t a0 = a_u32 + (uint32_t)(s >> 1) * A_KB + (uint32_t)(s & 1) * 2u * A_LBO;
+                    const uint32_t a0 = a_u32 + (uint32_t)ab * A_BUF + (uint32_t)(s >> 1) * A_KB + (uint32_t)(s & 1) * 2u * A_LBO;
                     const uint32_t b0 = ring_u32 + slot * stage_bytes;
                     const uint64_t a_hi = smem_desc(a0, A_LBO, 128), a_lo = smem_desc(a0 + A_PART, A_LBO, 128);
                     const uint64_t b_hi = smem_desc(b0, b_lbo, 128), b_lo = smem_desc(b0 + half_bytes, b_lbo, 128);
@@ -150,104 +190,25 @@ inter_fused_kernel(FusedParams P) {
                         load_w(r + P.nst);
                     }
                 }
-                mma_commit(smem_u32(&s_afree));  // A tiles of this chunk consumed
+                mma_commit(smem_u32(&s_afree[ab]));  // A tiles of this granule consumed
             }
             mma_commit(smem_u32(&s_accum));
         }
+        __syncwarp();  // the other 31 lanes sleep here instead of polling the accumulator barrier for the whole kernel
     } else {
         // ------------------------------------------------------------ producers
-
-        const int pt = tid / PT_THR, ptid = tid - pt * PT_THR;
-        const int a = ptid % FU_LANES, grp = ptid / FU_LANES;
+        const int aa = ptid % FU_LANES, grp = ptid / FU_LANES;
         const int k0 = grp * KG;
-        const bool a_ok = a < NA;
-        const int aa = a_ok ? a : a - 4;  // dead lanes shadow a live lane of their own warp (broadcast, no bank conflict)
-        const int pl = blockIdx.x * PTS + pt, pi = P.p_off + pl;
-        const float *F = HAS_FEATS ? P.feats + (size_t)z * P.c * P.p_in * NA : nullptr;
-        float *s_g = hdr + pt * NN * 6;
-        int32_t *s_idx = reinterpret_cast<int32_t *>(s_g + NN * 3);
-        float *s_mult = s_g + NN * 4;
-        int32_t *s_raw = reinterpret_cast<int32_t *>(s_g + NN * 5);
+        constexpr bool a_ok = true;
+        const float *F = P.feats + (size_t)z * P.c * P.p_in * NA;
+        const NeighbourList<C::CAP> &L = s_L[pt];
         float *Fp = Fs + (size_t)pt * 2 * CCH * NN * NA;
-        float *Gp = Gs + (size_t)pt * CKK * GSTR;
-
-        // distinct neighbours + multiplicities (see inter_group_tiles_kernel)
-        int nn = P.nn;
-        for (int n = ptid; n < NN; n += PT_THR) s_raw[n] = n < nn ? P.idx[((size_t)z * P.p + pi) * nn + n] : -1;
-        named_bar_sync(1, NPROD);
-        if (ptid < 32) {
-            const int n = ptid;
-            const int q = n < nn ? s_raw[n] : -1;
-            bool uniq = n < nn;
-            for (int m = 0; m < n && uniq; ++m) uniq = s_raw[m] != q;
-            int mult = 0;
-            for (int m = n; m < nn; ++m) mult += (s_raw[m] == q) ? 1 : 0;
-            const unsigned mask = __ballot_sync(0xffffffffu, uniq);
-            const int pos = __popc(mask & ((1u << n) - 1u));
-            if (uniq) {
-                const float *X = P.g.xyz + (size_t)z * 3 * P.p_in;
-                const float *Cn = P.g.centers + (size_t)z * 3 * P.p;
-                s_idx[pos] = q;
-                s_mult[pos] = (float)mult;
-                s_g[pos * 3] = X[q] - Cn[pi];
-                s_g[pos * 3 + 1] = X[P.p_in + q] - Cn[P.p + pi];
-                s_g[pos * 3 + 2] = X[2 * P.p_in + q] - Cn[2 * P.p + pi];
-            }
-            const int cnt = __popc(mask);
-            if (n >= cnt && n < NN) {
-                s_idx[n] = 0; s_mult[n] = 0.f;
-                s_g[n * 3] = 0.f; s_g[n * 3 + 1] = 0.f; s_g[n * 3 + 2] = 0.f;
-            }
-            if (n == 0) s_nu[pt] = cnt;
-        }
-        named_bar_sync(1, NPROD);
-        nn = s_nu[pt];  // number of DISTINCT neighbours of this point
-        for (int t = ptid; t < 2 * CCH * (NN - nn) * NA; t += PT_THR) {  // never-copied rows stay zero
-            const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
-            Fp[(bc * NN + n) * NA + e] = 0.f;
-        }
-
-        uint64_t w2[KG][NN / 2];
-        {
-            float R[9];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + aa * 9 + i);
-#pragma unroll
-            for (int i = 0; i < KG; ++i) {
-                const float kx = __ldg(P.g.kernels + (k0 + i) * 3), ky = __ldg(P.g.kernels + (k0 + i) * 3 + 1),
-                            kz = __ldg(P.g.kernels + (k0 + i) * 3 + 2);
-                const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
-                            rz = R[6] * kx + R[7] * ky + R[8] * kz;
-#pragma unroll
-                for (int n = 0; n < NN; n += 2) {
-                    float v[2];
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const float t = kernel_weight_fast(s_g[(n + e) * 3], s_g[(n + e) * 3 + 1], s_g[(n + e) * 3 + 2], rx, ry,
-                                                           rz, 1.0f / P.g.sigma);
-                        v[e] = (a_ok && n + e < nn) ? t * s_mult[n + e] : 0.f;
-                    }
-                    w2[i][n / 2] = pack_f32x2(v[0], v[1]);
-                }
-            }
-        }
+        const int total_nn = L.total;
+        constexpr int bar_id = 1;   // named barrier of the producer threads (points advance in lockstep)
 
         const uint32_t fs_u32 = smem_u32(Fp);
         const uint32_t gbar0 = smem_u32(&s_gbar[pt][0]);
-        constexpr uint32_t ROW_BYTES = NA * 4;
-        auto issue = [&](int chunk, int buf) {
-            if (!HAS_FEATS) return;
-            const uint32_t bar = gbar0 + 8u * (uint32_t)buf;
-            if (ptid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
-            for (int t = ptid; t < CCH * NN; t += PT_THR) {
-                const int cl = t / NN, n = t % NN;
-                if (n < nn)
-                    bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
-                             F + ((size_t)(chunk * CCH + cl) * P.p_in + s_idx[n]) * NA, ROW_BYTES, bar);
-            }
-        };
-
-        // addressing of the conversion pass that does not depend on the chunk
+        // A-tile row of this thread: address of its 16-byte piece of K' chunk 0 of buffer 0
         const uint32_t a_row = smem_u32(a_tiles) + (uint32_t)(pt * 64 + aa) * 16u;
         uint8_t *keep_base = nullptr;
         if (P.keep != nullptr) {
@@ -256,78 +217,189 @@ inter_fused_kernel(FusedParams P) {
             keep_base = P.keep + (size_t)zs * P.keep_slab_bytes + ((size_t)(row >> 7) * P.keep_k_blocks) * tile_bytes(TR_A) +
                         (size_t)(row & 127) * 16;
         }
-
-        uint32_t phase_bits = 0u;
-        // the expect_tx of a buffer must be posted before any of its copies can complete: ptid 0 arms the barrier,
-        // then everybody copies (named barrier keeps the order)
-        issue(0, 0);
-        for (int chunk = 0; chunk < nchunks; ++chunk) {
-            const int buf = chunk & 1;
-            if (chunk + 1 < nchunks) issue(chunk + 1, buf ^ 1);
-            if (HAS_FEATS) {
-                mbar_wait(gbar0 + 8u * (uint32_t)buf, (phase_bits >> buf) & 1u);
-                phase_bits ^= 1u << buf;
+        // one 16-byte hi piece + one lo piece of K' chunk `kc` (global numbering) = granule-local chunk `kcl`
+        auto put = [&](int ab, int kcl, int kc, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t h3, uint32_t l0, uint32_t l1,
+                       uint32_t l2, uint32_t l3) {
+            if (!a_ok) return;
+            const uint32_t dst = a_row + (uint32_t)ab * A_BUF + (uint32_t)(kcl >> 2) * A_KB + (uint32_t)(kcl & 3) * A_LBO;
+            st_shared_v4(dst, h0, h1, h2, h3);
+            st_shared_v4(dst + A_PART, l0, l1, l2, l3);
+            if (keep_base != nullptr) {
+                uint8_t *kd = keep_base + (size_t)(kc >> 2) * tile_bytes(TR_A) + (size_t)(kc & 3) * (TR_A * 16);
+                *reinterpret_cast<uint4 *>(kd) = make_uint4(h0, h1, h2, h3);
+                *reinterpret_cast<uint4 *>(kd + part_bytes(TR_A)) = make_uint4(l0, l1, l2, l3);
             }
-            // ---- spatial contraction of CCH channels
-            const float *fbase = Fp + (size_t)(buf * CCH * NN) * NA + aa;
-            float *gbase = Gp + (size_t)k0 * GSTR + aa;
-#pragma unroll 2
-            for (int cl = 0; cl < CCH; ++cl) {
-                uint64_t acc2[KG];
+        };
+
+        int ci = 0;  // gather chunks issued so far by this point (buffer = ci & 1, parity = (ci >> 1) & 1)
+        int gi = 0;  // granules produced so far by this CTA
+        const int nchunks = P.c / CCH;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int n_first = pass * NN;
+            int nn = total_nn - n_first;          // distinct neighbours of this pass
+            nn = nn < 0 ? 0 : (nn > NN ? NN : nn);
+            named_bar_sync(bar_id, NPROD);      // everybody is done with the previous pass's gather buffers
+            for (int t = ptid; t < 2 * CCH * (NN - nn) * NA; t += PT_THR) {  // never-copied rows are zero
+                const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
+                Fp[(bc * NN + n) * NA + e] = 0.f;
+            }
+            uint64_t w2[KG][NN / 2];
+            {
+                float R[9];
 #pragma unroll
-                for (int i = 0; i < KG; ++i) acc2[i] = 0ull;
-                const float *frow = fbase + cl * NN * NA;
+                for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + aa * 9 + i);
+                const float inv_sigma = 1.0f / P.g.sigma;
 #pragma unroll
-                for (int n4 = 0; n4 < NN; n4 += 4) {
-                    if (n4 < nn) {
+                for (int i = 0; i < KG; ++i) {
+                    const float kx = __ldg(P.g.kernels + (k0 + i) * 3), ky = __ldg(P.g.kernels + (k0 + i) * 3 + 1),
+                                kz = __ldg(P.g.kernels + (k0 + i) * 3 + 2);
+                    const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
+                                rz = R[6] * kx + R[7] * ky + R[8] * kz;
 #pragma unroll
-                        for (int n = n4; n < n4 + 4; n += 2) {
-                            const uint64_t f2 = HAS_FEATS ? pack_f32x2(frow[n * NA], frow[(n + 1) * NA]) : pack_f32x2(1.0f, 1.0f);
+                    for (int n = 0; n < NN; n += 2) {
+                        float v[2];
 #pragma unroll
-                            for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(w2[i][n / 2], f2, acc2[i]);
+                        for (int e = 0; e < 2; ++e) {
+                            const int m = MODE == 1 ? n + e : n_first + n + e;
+                            const float t = kernel_weight_fast(L.g[m * 3], L.g[m * 3 + 1], L.g[m * 3 + 2], rx, ry, rz, inv_sigma);
+                            v[e] = (a_ok && n + e < nn) ? t * L.mult[m] : 0.f;
+                        }
+                        w2[i][n / 2] = pack_f32x2(v[0], v[1]);
+                    }
+                }
+            }
+            auto issue = [&](int chunk) {  // gather chunk `chunk` of this pass into buffer ci & 1
+                const int buf = ci & 1;
+                const uint32_t bar = gbar0 + 8u * (uint32_t)buf;
+                if (ptid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
+                for (int t = ptid; t < CCH * NN; t += PT_THR) {
+                    const int cl = t / NN, n = t % NN;
+                    if (n < nn)
+                        bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
+                                 F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA, ROW_BYTES, bar);
+                }
+                ++ci;
+            };
+            named_bar_sync(bar_id, NPROD);  // zero rows of both buffers are in place before the FMA loops read them
+            issue(0);
+            for (int g = 0; g < ngran; ++g, ++gi) {
+                const int ab = gi & 1;
+                uint32_t hi[12], lo[12];
+#pragma unroll
+                for (int h = 0; h < CH_G; ++h) {
+                    const int chunk = g * CH_G + h;
+                    const int cur = ci - 1;          // the chunk about to be consumed was issued last
+                    const int buf = cur & 1;
+                    named_bar_sync(bar_id, NPROD);  // every thread of the point is done with the other gather buffer
+                    if (chunk + 1 < nchunks) issue(chunk + 1);
+                    mbar_wait(gbar0 + 8u * (uint32_t)buf, (uint32_t)(cur >> 1) & 1u);
+                    if (h == 0 && gi >= 2)  // the MMAs of granule gi-2 have read A[ab]
+                        mbar_wait(smem_u32(&s_afree[ab]), (uint32_t)((gi >> 1) - 1) & 1u);
+                    const float *fbase = Fp + (size_t)(buf * CCH * NN) * NA + aa;
+                    if (MODE == 1) {
+                        // 4 channels x 6 kernel points = 24 values = K' chunks 12 g + 3 grp + {0,1,2}
+                        const int kcl0 = grp * 3, kc0 = g * 12 + grp * 3;
+#pragma unroll
+                        for (int cl4 = 0; cl4 < 4; ++cl4) {
+                            uint64_t acc2[KG];
+#pragma unroll
+                            for (int i = 0; i < KG; ++i) acc2[i] = 0ull;
+                            const float *frow = fbase + cl4 * NN * NA;
+#pragma unroll
+                            for (int n4 = 0; n4 < NN; n4 += 4) {
+                                if (n4 < nn) {
+#pragma unroll
+                                    for (int n = n4; n < n4 + 4; n += 2) {
+                                        const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
+#pragma unroll
+                                        for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(w2[i][n / 2], f2, acc2[i]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int ip = 0; ip < KG / 2; ++ip) {
+                                float e0, o0, e1, o1;
+                                unpack_f32x2(acc2[2 * ip], e0, o0);
+                                unpack_f32x2(acc2[2 * ip + 1], e1, o1);
+                                const float v0 = e0 + o0, v1 = e1 + o1;
+                                const __nv_bfloat162 hp = __floats2bfloat162_rn(v0, v1);
+                                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
+                                const __nv_bfloat162 lp = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+                                hi[cl4 * 3 + ip] = hb;
+                                lo[cl4 * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                            }
+                            if (cl4 >= 1) {  // 6 (cl4 + 1) values so far: piece j = cl4 - 1 (values 8j .. 8j+7) is complete
+                                const int jj = cl4 - 1;
+                                put(ab, kcl0 + jj, kc0 + jj, hi[4 * jj], hi[4 * jj + 1], hi[4 * jj + 2], hi[4 * jj + 3], lo[4 * jj],
+                                    lo[4 * jj + 1], lo[4 * jj + 2], lo[4 * jj + 3]);
+                            }
+                        }
+                    } else {
+                        // 8 channels (two chunks) x 3 kernel points = 24 values = K' chunks 24 g + 3 grp + {0,1,2}
+#pragma unroll
+                        for (int cp = 0; cp < CCH / 2; ++cp) {  // two channels -> 6 values -> 3 packed pairs
+                            uint64_t acc2[2][KG];
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                                for (int i = 0; i < KG; ++i) acc2[q][i] = 0ull;
+#pragma unroll
+                            for (int n4 = 0; n4 < NN; n4 += 4) {
+                                if (n4 < nn) {
+#pragma unroll
+                                    for (int n = n4; n < n4 + 4; n += 2) {
+#pragma unroll
+                                        for (int q = 0; q < 2; ++q) {
+                                            const float *frow = fbase + (cp * 2 + q) * NN * NA;
+                                            const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
+#pragma unroll
+                                            for (int i = 0; i < KG; ++i) acc2[q][i] = fma_f32x2(w2[i][n / 2], f2, acc2[q][i]);
+                                        }
+                                    }
+                                }
+                            }
+                            float v[6];
+#pragma unroll
+                            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                                for (int i = 0; i < KG; ++i) {
+                                    float e, o;
+                                    unpack_f32x2(acc2[q][i], e, o);
+                                    v[q * KG + i] = e + o;
+                                }
+#pragma unroll
+                            for (int ip = 0; ip < 3; ++ip) {
+                                const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * ip], v[2 * ip + 1]);
+                                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
+                                const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * ip] - __uint_as_float(hb << 16),
+                                                                                v[2 * ip + 1] - __uint_as_float(hb & 0xffff0000u));
+                                hi[h * 6 + cp * 3 + ip] = hb;
+                                lo[h * 6 + cp * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                            }
+                        }
+                        const int kcl0 = grp * 3, kc0 = g * 24 + grp * 3;
+                        if (h == 0) {
+                            put(ab, kcl0, kc0, hi[0], hi[1], hi[2], hi[3], lo[0], lo[1], lo[2], lo[3]);
+                        } else {
+                            put(ab, kcl0 + 1, kc0 + 1, hi[4], hi[5], hi[6], hi[7], lo[4], lo[5], lo[6], lo[7]);
+                            put(ab, kcl0 + 2, kc0 + 2, hi[8], hi[9], hi[10], hi[11], lo[8], lo[9], lo[10], lo[11]);
                         }
                     }
                 }
-                if (a_ok) {
-#pragma unroll
-                    for (int i = 0; i < KG; ++i) {
-                        float e, o;
-                        unpack_f32x2(acc2[i], e, o);
-                        gbase[(cl * FU_KS + i) * GSTR] = e + o;
-                    }
-                }
+                // granule complete: publish this warp's pieces to the tensor core
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&s_afull[ab]));
             }
-            named_bar_sync(1, NPROD);  // staging complete; every thread is done with Fs[buf]
-            if (chunk > 0) mbar_wait(smem_u32(&s_afree), (uint32_t)(chunk - 1) & 1u);  // MMAs of the previous chunk have read A
-            // ---- fp32 staging -> bf16 hi/lo operand tiles in shared memory (+ global copy for the weight gradient)
-            if (a_ok) {
-                for (int kc = grp; kc < CKK / 8; kc += GROUPS) {
-                    float x[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) x[i] = Gp[(kc * 8 + i) * GSTR + aa];
-                    uint4 hi, lo;
-                    split8(x, hi, lo);
-                    const uint32_t dst = a_row + (uint32_t)(kc >> 2) * A_KB + (uint32_t)(kc & 3) * A_LBO;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(hi.x), "r"(hi.y), "r"(hi.z), "r"(hi.w) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + A_PART), "r"(lo.x), "r"(lo.y), "r"(lo.z), "r"(lo.w) : "memory");
-                    if (keep_base != nullptr) {
-                        const int kkg = chunk * CKK + kc * 8;
-                        uint8_t *kd = keep_base + (size_t)(kkg >> 5) * tile_bytes(TR_A) + (size_t)((kkg & 31) >> 3) * (TR_A * 16);
-                        *reinterpret_cast<uint4 *>(kd) = hi;
-                        *reinterpret_cast<uint4 *>(kd + part_bytes(TR_A)) = lo;
-                    }
-                }
-            }
-            fence_proxy_async_smem();  // generic-proxy tile writes -> visible to the tensor core
-            named_bar_sync(1, NPROD);
-            if (tid == 0) mbar_arrive(smem_u32(&s_afull));
         }
 
-        // ------------------------------------------------------------ epilogue: TMEM -> out[z, o, p, a]
+    }
+    {
+        // ------------------------------------------------------------ epilogue: TMEM -> out[z, o, p, a], all 16 warps
         mbar_wait(smem_u32(&s_accum), 0);
         tc_fence_after();
-        constexpr int NWARPS = NPROD / 32;
-        const int lane = tid & 31, q = warp & 3;       // TMEM lane quarter of this warp
+        constexpr int NA = FU_NA;
+        const int q = warp & 3;                          // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                  // = pt*64 + anchor
         const int rpt = row >> 6, ra = row & 63;
         if (rpt < PTS) {                                // warp-uniform (PTS == 1: quarters 2,3 hold dead rows)
@@ -347,36 +419,41 @@ inter_fused_kernel(FusedParams P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == NPROD / 32) {
+    if (warp == NPWARPS) {
         tc_fence_after();
         tmem_dealloc(tmem_base, P.tmem_cols);
     }
 }
 
-template <int NN, int KG, int CCH, int PTS, bool HAS_FEATS>
+template <int MODE>
 int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
-    constexpr int NPROD = PTS * FU_LANES * (FU_KS / KG);
-    constexpr int CKK = CCH * FU_KS;
-    constexpr size_t A_BYTES = (size_t)(CKK / 32) * 2 * 4 * (PTS * 64) * 16 + (PTS == 1 ? 1024 : 0);
-    const size_t fixed = A_BYTES + sizeof(float) * (size_t)PTS * (2 * CCH * NN * FU_NA + CKK * (FU_NA + 1) + NN * 6) + 128;
+    using C = FuCfg<MODE>;
+    constexpr int NPROD = C::PTS * FU_LANES * (FU_KS / C::KG);
+    constexpr int ROWS = C::PTS * 64;
+    constexpr size_t A_BYTES = (size_t)2 * (C::GCH * FU_KS / 32) * 2 * 4 * ROWS * 16 + (C::PTS == 1 ? 1024 : 0);
+    const size_t fixed = A_BYTES + sizeof(float) * (size_t)C::PTS * 2 * FU_CCH * C::NN * FU_NA;
     const size_t stage = (size_t)P.trb * 64;
-    const size_t budget = 227 * 1024 - 1024;  // static shared memory (barriers) comes on top
+    const size_t budget = 227 * 1024 - 6 * 1024;  // static shared memory (neighbour lists, barriers) comes on top
     if (fixed + 2 * stage > budget) return 1;
     int nst = (int)((budget - fixed) / stage);
     if (nst > 8) nst = 8;
     P.nst = nst;
     const size_t smem_bytes = fixed + (size_t)nst * stage;
     static DynSmemOnce once;  // one per template instantiation
-    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<NN, KG, CCH, PTS, HAS_FEATS>, 227 * 1024 - 1024, "inter_fused_kernel")) return rc;
-    dim3 grid(p_cnt / PTS, bc);
-    inter_fused_kernel<NN, KG, CCH, PTS, HAS_FEATS><<<grid, NPROD + 128, smem_bytes, s>>>(P);
+    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE>, (int)budget, "inter_fused_kernel")) return rc;
+    dim3 grid(p_cnt / C::PTS, bc);
+    inter_fused_kernel<MODE><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
     return check_launch("inter_fused_kernel");
 }
 
 }  // namespace
 
-bool inter_fused_ok(int c, int c_out, int p_cnt, int nn, int na, int ks) {
-    return ks == FU_KS && na == FU_NA && nn <= 32 && c >= 4 && c % 4 == 0 && c_out <= 256 && (nn > 16 || p_cnt % 2 == 0);
+// K' mode the fused kernel uses for this shape (0 = shape not covered).  keep = the caller wants the operand tiles.
+int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool keep) {
+    if (ks != FU_KS || na != FU_NA || c_out > 256 || c < 4) return 0;
+    if (nn <= 16 && c % 4 == 0 && p_cnt % 2 == 0) return 1;
+    if (nn <= (keep ? 32 : DEDUP_MAX_RAW) && c % 8 == 0) return 2;
+    return 0;
 }
 
 // Returns 1 when the shape is not covered (the caller takes the grouping-kernel + GEMM route).
@@ -384,7 +461,8 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
                        long long out_stride_z, long long out_stride_o, void *keep_tiles, int keep_k_blocks,
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt, int bc, int c, int c_out, int p_in, int p, int nn,
                        int na, int ks, cudaStream_t s) {
-    if (!inter_fused_ok(c, c_out, p_cnt, nn, na, ks) || bc > 65535 || feats == nullptr) return 1;
+    const int mode = inter_fused_mode(c, c_out, p_cnt, nn, na, ks, keep_tiles != nullptr);
+    if (mode == 0 || bc > 65535 || feats == nullptr) return 1;
     FusedParams P;
     P.feats = feats;
     P.idx = idx;
@@ -404,8 +482,8 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
     while ((int)cols < P.trb) cols *= 2;
     P.tmem_cols = cols;
     ProfScope prof(s, KC_INTER_FUSED);
-    if (nn <= 16) return launch_fused_variant<16, 6, 4, 2, true>(P, p_cnt, bc, s);
-    return launch_fused_variant<32, 3, 4, 1, true>(P, p_cnt, bc, s);
+    if (mode == 1) return launch_fused_variant<1>(P, p_cnt, bc, s);
+    return launch_fused_variant<2>(P, p_cnt, bc, s);
 }
 
 }  // namespace epn

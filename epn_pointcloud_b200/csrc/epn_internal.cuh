@@ -81,7 +81,7 @@ int launch_inter_group_tiles(const float *feats, const int32_t *idx, const Inter
 // (z, o, pl, a) at out + z*out_stride_z + o*out_stride_o + pl*na + a.  keep_tiles (optional): the operand tiles
 // for the weight gradient, clouds stored in slabs of keep_slab_clouds (keep_slab_bytes apart), rows
 // (z % keep_slab_clouds)*keep_cols_per_z + pl*na + a.  Returns 1 if the shape is unsupported.
-bool inter_fused_ok(int c, int c_out, int p_cnt, int nn, int na, int ks);
+int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool keep);  // 0 = not covered, else the K' mode
 int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &g, const void *w_tiles, float *out,
                        long long out_stride_z, long long out_stride_o, void *keep_tiles, int keep_k_blocks,
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt,

@@ -471,6 +471,35 @@ def test_fused_inter_conv_matches_two_kernel_schedule(E, c_in, c_out, p_in, stri
         assert rel_err(a, b_) < 3e-5, name
 
 
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_", [(32, 64, 512, 2, 64), (64, 128, 256, 1, 64), (16, 32, 512, 2, 128),
+                                                        (128, 256, 128, 2, 40)])
+def test_fused_inter_conv_many_distinct_neighbours(E, c_in, c_out, p_in, stride, nn_):
+    """Rows of 40 / 64 / 128 slots that are ALL distinct (radius 1.2 on the unit sphere): the fused inference kernel
+    runs 2-4 passes of 32 neighbours into the same TMEM accumulator; the training forward takes the grouping kernels
+    (the 64-distinct-neighbour kernel, or the generic path for 128) + GEMM.  Both against the fp32 SIMT engine."""
+    conv = _layer(E, c_in, c_out, stride, nn_, 1.2, 0.5)
+    xyz = sphere(2, p_in, 29).to(DEV)
+    f = torch.randn(2, c_in, p_in, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(7))
+    idx, _, _, _ = conv(E.SphericalPointCloud(xyz, f, None))
+    assert int(idx[0, 0].unique().numel()) > 32          # more distinct neighbours than one pass holds
+    outs = {}
+    for backend in ("simt", "umma"):
+        E.ops.set_gemm_backend(backend)
+        try:
+            fg = f.clone().requires_grad_(True)
+            conv.zero_grad()
+            y = conv(E.SphericalPointCloud(xyz, fg, None))[3].feats
+            r = torch.randn(y.shape, device=DEV, generator=torch.Generator(DEV).manual_seed(8))
+            (y * r).sum().backward()
+            with torch.no_grad():
+                y2 = conv(E.SphericalPointCloud(xyz, f, None))[3].feats
+            outs[backend] = (y.detach(), fg.grad.detach(), conv.basic_conv.W.grad.detach().clone(), y2)
+        finally:
+            E.ops.set_gemm_backend("umma")
+    for a, b_, name in zip(outs["umma"], outs["simt"], ("out", "dfeats", "dW", "out_no_grad")):
+        assert rel_err(a, b_) < 3e-5, name
+
+
 @pytest.mark.parametrize("c_in,c_out,p", [(4, 8, 32), (64, 64, 512), (128, 128, 256), (256, 256, 128), (5, 300, 17)])
 def test_umma_engine_matches_simt_intra(E, both_backends, c_in, c_out, p):
     torch.manual_seed(0)
