@@ -170,10 +170,10 @@ struct ColsView {
 constexpr long long HUGE_Z = 1LL << 60;
 
 static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s,
-                        int kperm = 0) {
+                        int kperm = 0, int step_layout = 0) {
     if (gemm_backend() != 0) return 0;
     if (fwd && kperm) {
-        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), kperm, s);
+        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), kperm, step_layout, s);
         if (rc) return rc;
     } else if (fwd) {
         SplitSrc src{W, HUGE_Z, 0, ck, HUGE_Z, 0, 1};
@@ -418,7 +418,7 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
         EPN_REQUIRE_PTR(grouped_layout);
         *grouped_layout = encode_layout(kperm, sp);
     }
-    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm));
+    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm, fused ? 1 : 0));
     if (fused) {
         // kept tiles (training) keep the slab layout the weight-gradient pass expects
         InterGeom g{xyz, centers, anchors, kernels, sigma};

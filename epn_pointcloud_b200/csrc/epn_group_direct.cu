@@ -532,7 +532,7 @@ inter_group_occ_kernel(const float *__restrict__ feats, const int32_t *__restric
 // Weight tiles of the forward GEMM (rows = c_out in trb-row tiles) with K in the permuted order K'(c,k).
 __global__ void __launch_bounds__(256)
 inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_out, int ck, int trb, int k_blocks,
-                           int mode) {
+                           int mode, int steps) {
     const int row = blockIdx.x * 32 + (threadIdx.x & 31), kcg = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int rows_pad = (c_out + trb - 1) / trb * trb;
     if (row >= rows_pad || kcg >= k_blocks * (KB / 8)) return;
@@ -545,16 +545,24 @@ inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ ds
     uint4 hi, lo;
     split8(x, hi, lo);
     const int rt = row / trb, r = row - rt * trb;
+    if (steps) {
+        // "step" layout of the fused inter kernel (one row tile): every 16-wide k step is one contiguous block
+        // [hi: 2 k-chunks x trb rows x 16 B][lo: same] so that ONE bulk copy moves a pipeline stage
+        uint8_t *blk = dst + (size_t)(kcg >> 1) * trb * 64 + (size_t)(kcg & 1) * trb * 16 + (size_t)r * 16;
+        *reinterpret_cast<uint4 *>(blk) = hi;
+        *reinterpret_cast<uint4 *>(blk + (size_t)trb * 32) = lo;
+        return;
+    }
     uint8_t *tile = dst + ((size_t)rt * k_blocks + (kcg >> 2)) * tile_bytes(trb);
     *reinterpret_cast<uint4 *>(tile + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = hi;
     *reinterpret_cast<uint4 *>(tile + part_bytes(trb) + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = lo;
 }
 
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, cudaStream_t s) {
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s) {
     const int k_blocks = (ck + KB - 1) / KB, rows_pad = (c_out + trb - 1) / trb * trb;
     dim3 grid((rows_pad + 31) / 32, (k_blocks * (KB / 8) + 7) / 8);
     ProfScope prof(s, KC_SPLIT);
-    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks, mode);
+    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks, mode, steps);
     return check_launch("inter_w_tiles_kperm_kernel");
 }
 

@@ -25,6 +25,8 @@
 //           32 neighbours, accumulating into the same TMEM tile (the GEMM is linear in G).
 // In training the producers also write their pieces to global memory (the operand tiles the weight-gradient GEMM
 // consumes, epn_gemm_dw.cu); that needs the complete G of a point in one pass, i.e. rows of <= 32 slots.
+#include <stdlib.h>
+
 #include "epn_dedup.cuh"
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
@@ -55,7 +57,7 @@ struct FusedParams {
     int keep_k_blocks, keep_slab_clouds;   // clouds z are stored in slabs of keep_slab_clouds, each slab a tile matrix
     long long keep_cols_per_z;
     size_t keep_slab_bytes;
-    int c, c_out, p_in, p, nn, p_off, trb, nst;
+    int c, c_out, p_in, p, nn, p_off, trb, nst, sps;   // sps: 16-k steps per weight-ring stage (1, 2 or 3)
     uint32_t tmem_cols;
 };
 
@@ -66,7 +68,12 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
-template <int MODE>
+// GATHER: how the neighbours' 240-byte feature rows reach shared memory
+//   0  one bulk copy (UBLKCP) per row, issued by the first 64 (MODE 1) / 128 (MODE 2) threads of the point
+//   1  one bulk copy per row, rows dealt round-robin to ALL threads of the point (a warp issues its lanes' copies
+//      one at a time, so spreading them shortens the slowest warp's issue phase)
+//   2  15 cp.async of 16 bytes per row by all threads + mbarrier arrive.noinc
+template <int MODE, int GATHER>
 __global__ void __launch_bounds__(FuCfg<MODE>::PTS *FU_LANES *(FU_KS / FuCfg<MODE>::KG) + FU_CTRL, 1)  // 480 + 32
 inter_fused_kernel(FusedParams P) {
     using C = FuCfg<MODE>;
@@ -87,14 +94,13 @@ inter_fused_kernel(FusedParams P) {
     constexpr uint32_t A_KB = 2 * A_PART;         // one k-block
     constexpr uint32_t A_BUF = KBG * A_KB;        // one granule
     constexpr uint32_t A_BYTES = 2 * A_BUF + (PTS == 1 ? 1024 : 0);  // PTS == 1: the M=128 MMA over-reads 64 dead rows
-    constexpr uint32_t ROW_BYTES = NA * 4;
 
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *a_tiles = smem;                                               // [2][KBG] k-blocks
     float *Fs = reinterpret_cast<float *>(smem + A_BYTES);                 // [PTS][2][CCH][NN][NA]
     uint8_t *ring = reinterpret_cast<uint8_t *>(Fs + PTS * 2 * CCH * NN * NA);  // weight ring, nst stages
     __shared__ NeighbourList<C::CAP> s_L[PTS];
-    __shared__ __align__(8) uint64_t s_gbar[PTS][2];   // gather buffers
+    __shared__ __align__(8) uint64_t s_gbar[PTS][2];   // gather buffers: bytes landed
     __shared__ __align__(8) uint64_t s_wfull[8], s_wempty[8];
     __shared__ __align__(8) uint64_t s_afull[2], s_afree[2], s_accum;
     __shared__ uint32_t s_tmem;
@@ -103,13 +109,15 @@ inter_fused_kernel(FusedParams P) {
     const int warp = tid >> 5, lane = tid & 31;
     const bool is_ctrl = tid >= NPROD;
     const int z = blockIdx.y;
-    const uint32_t stage_bytes = (uint32_t)P.trb * 64u;  // 16 k of hi + 16 k of lo
+    const uint32_t step_bytes = (uint32_t)P.trb * 64u;   // 16 k of hi + 16 k of lo
+    const uint32_t stage_bytes = step_bytes * (uint32_t)P.sps;
     const int ngran = P.c / GCH;                          // granules per pass
 
     if (tid == 0) {
         for (int i = 0; i < PTS; ++i) {
-            mbar_init(smem_u32(&s_gbar[i][0]), 1);
-            mbar_init(smem_u32(&s_gbar[i][1]), 1);
+            // GATHER 2: one (cp.async-tracking) arrival per thread of the point; else one arrive.expect_tx
+            mbar_init(smem_u32(&s_gbar[i][0]), GATHER == 2 ? PT_THR : 1);
+            mbar_init(smem_u32(&s_gbar[i][1]), GATHER == 2 ? PT_THR : 1);
         }
         for (int i = 0; i < P.nst; ++i) {
             mbar_init(smem_u32(&s_wfull[i]), 1);
@@ -149,48 +157,79 @@ inter_fused_kernel(FusedParams P) {
     if (is_ctrl) {
         // ------------------------------------------------------------ control warp: W ring + MMA issue (one thread)
         if (tid == NPROD) {
-            const int total_steps = total_gran * STEPS_G, steps_pass = ngran * STEPS_G;
+            // One thread feeds the tensor pipe, so this loop is written for instruction count: no divisions, slot /
+            // parity counters advanced incrementally, descriptors = constant base + small offset (a 16-k step of a
+            // C_out = 64 layer is only 96 tensor-core cycles; the first version of this loop spent ~1800 cycles of
+            // dependent scalar code per step and starved the producers of A buffers).
+            const uint32_t sps = (uint32_t)P.sps;                      // 16-k steps per ring stage (divides STEPS_G)
+            const int stages_g = STEPS_G / (int)sps;                   // ring stages per granule
+            const int total_stages = total_gran * stages_g, stages_pass = ngran * stages_g;
             const uint32_t ring_u32 = smem_u32(ring);
             const uint32_t half_bytes = (uint32_t)P.trb * 32u;
-            const size_t w_tile = tile_bytes(P.trb), w_part = part_bytes(P.trb);
-            auto load_w = [&](int j) {  // 16-k step j -> ring slot j % nst (every pass re-streams W)
-                const int slot = j % P.nst, jw = j % steps_pass;
-                const uint32_t bar = smem_u32(&s_wfull[slot]);
-                const uint8_t *src = P.Wt + (size_t)(jw >> 1) * w_tile + (size_t)(jw & 1) * half_bytes;
+            const uint32_t nst = (uint32_t)P.nst;
+            const uint32_t wfull0 = smem_u32(&s_wfull[0]), wempty0 = smem_u32(&s_wempty[0]);
+            // weight tiles in "step" layout (launch_inter_w_tiles_kperm, steps = 1): 16-k step jw is ONE contiguous
+            // block [hi: 2 k-chunks x trb rows][lo: ...] of step_bytes, so a stage of `sps` steps is one bulk copy
+            const uint8_t *wsrc = P.Wt;
+            int jw_load = 0;             // stage (within the pass) the next load fetches
+            uint32_t lslot = 0;          // ring slot the next load fills
+            auto load_w = [&]() {
+                const uint32_t bar = wfull0 + 8u * lslot;
                 mbar_arrive_expect_tx(bar, stage_bytes);
-                bulk_g2s(ring_u32 + slot * stage_bytes, src, half_bytes, bar);
-                bulk_g2s(ring_u32 + slot * stage_bytes + half_bytes, src + w_part, half_bytes, bar);
+                bulk_g2s(ring_u32 + lslot * stage_bytes, wsrc, stage_bytes, bar);
+                wsrc += stage_bytes;
+                if (++jw_load == stages_pass) { jw_load = 0; wsrc = P.Wt; }   // every pass re-streams W
+                if (++lslot == nst) lslot = 0;
             };
-            for (int j = 0; j < P.nst && j < total_steps; ++j) load_w(j);
+            int loaded = 0;
+            for (; loaded < (int)nst && loaded < total_stages; ++loaded) load_w();
             const uint32_t idesc = instr_desc_bf16_m128(P.trb);
             const uint32_t b_lbo = (uint32_t)P.trb * 16u;
-            const uint32_t a_u32 = smem_u32(a_tiles);
-            int j = 0;
+            const uint64_t a_desc0 = smem_desc(smem_u32(a_tiles), A_LBO, 128);      // + (byte offset >> 4)
+            const uint64_t b_desc0 = smem_desc(ring_u32, b_lbo, 128);
+            const uint32_t stage16 = stage_bytes >> 4, step16 = step_bytes >> 4, half16 = half_bytes >> 4;
+            uint32_t slot = 0, wpar = 0;     // slot / parity of the stage being consumed
+            uint32_t eslot = 0, epar = 0;    // slot / parity of the stage whose MMAs are awaited before its slot is refilled
+            uint32_t accumulate = 0, sub = 0;
+            bool first = true;
+            const uint32_t afull0 = smem_u32(&s_afull[0]), afree0 = smem_u32(&s_afree[0]);
             for (int gi = 0; gi < total_gran; ++gi) {
-                const int ab = gi & 1;
-                mbar_wait(smem_u32(&s_afull[ab]), (uint32_t)(gi >> 1) & 1u);
+                const uint32_t ab = (uint32_t)gi & 1u;
+                mbar_wait_q(afull0 + 8u * ab, ((uint32_t)gi >> 1) & 1u);
                 tc_fence_after();
-                for (int s = 0; s < STEPS_G; ++s, ++j) {
-                    const int slot = j % P.nst;
-                    mbar_wait(smem_u32(&s_wfull[slot]), (uint32_t)(j / P.nst) & 1u);
-                    tc_fence_after();
-                    const uint32_t a0 = a_u32 + (uint32_t)ab * A_BUF + (uint32_t)(s >> 1) * A_KB + (uint32_t)(s & 1) * 2u * A_LBO;
-                    const uint32_t b0 = ring_u32 + slot * stage_bytes;
-                    const uint64_t a_hi = smem_desc(a0, A_LBO, 128), a_lo = smem_desc(a0 + A_PART, A_LBO, 128);
-                    const uint64_t b_hi = smem_desc(b0, b_lbo, 128), b_lo = smem_desc(b0 + half_bytes, b_lbo, 128);
-                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, j != 0);
+                const uint64_t a_g = a_desc0 + (uint64_t)(ab * (A_BUF >> 4));
+#pragma unroll
+                for (int s = 0; s < STEPS_G; ++s) {
+                    if (sub == 0) {
+                        mbar_wait_q(wfull0 + 8u * slot, wpar);
+                        tc_fence_after();
+                    }
+                    const uint64_t a_hi = a_g + (uint64_t)((uint32_t)(s >> 1) * (A_KB >> 4) + (uint32_t)(s & 1) * (2u * A_LBO >> 4));
+                    const uint64_t a_lo = a_hi + (uint64_t)(A_PART >> 4);
+                    const uint64_t b_hi = b_desc0 + (uint64_t)(slot * stage16 + sub * step16);
+                    const uint64_t b_lo = b_hi + (uint64_t)half16;
+                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, accumulate);
+                    accumulate = 1;
                     mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, 1);
                     mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, 1);
-                    mma_commit(smem_u32(&s_wempty[slot]));
-                    // refill the slot of the PREVIOUS step (its MMAs finish before this step's do, so this wait
-                    // does not drain the tensor pipe)
-                    const int r = j - 1;
-                    if (r >= 0 && r + P.nst < total_steps) {
-                        mbar_wait(smem_u32(&s_wempty[r % P.nst]), (uint32_t)(r / P.nst) & 1u);
-                        load_w(r + P.nst);
+                    if (++sub == sps) {
+                        sub = 0;
+                        mma_commit(wempty0 + 8u * slot);
+                        if (++slot == nst) { slot = 0; wpar ^= 1u; }
+                        // refill the slot of the PREVIOUS stage (its MMAs finish before this stage's do, so this wait
+                        // does not drain the tensor pipe)
+                        if (!first) {
+                            if (loaded < total_stages) {
+                                mbar_wait_q(wempty0 + 8u * eslot, epar);
+                                load_w();
+                                ++loaded;
+                            }
+                            if (++eslot == nst) { eslot = 0; epar ^= 1u; }
+                        }
+                        first = false;
                     }
                 }
-                mma_commit(smem_u32(&s_afree[ab]));  // A tiles of this granule consumed
+                mma_commit(afree0 + 8u * ab);  // A tiles of this granule consumed
             }
             mma_commit(smem_u32(&s_accum));
         }
@@ -208,6 +247,8 @@ inter_fused_kernel(FusedParams P) {
 
         const uint32_t fs_u32 = smem_u32(Fp);
         const uint32_t gbar0 = smem_u32(&s_gbar[pt][0]);
+        const uint32_t afree0 = smem_u32(&s_afree[0]), afull0 = smem_u32(&s_afull[0]);
+
         // A-tile row of this thread: address of its 16-byte piece of K' chunk 0 of buffer 0
         const uint32_t a_row = smem_u32(a_tiles) + (uint32_t)(pt * 64 + aa) * 16u;
         uint8_t *keep_base = nullptr;
@@ -239,10 +280,8 @@ inter_fused_kernel(FusedParams P) {
             int nn = total_nn - n_first;          // distinct neighbours of this pass
             nn = nn < 0 ? 0 : (nn > NN ? NN : nn);
             named_bar_sync(bar_id, NPROD);      // everybody is done with the previous pass's gather buffers
-            for (int t = ptid; t < 2 * CCH * (NN - nn) * NA; t += PT_THR) {  // never-copied rows are zero
-                const int e = t % NA, r = t / NA, n = nn + r % (NN - nn), bc = r / (NN - nn);
-                Fp[(bc * NN + n) * NA + e] = 0.f;
-            }
+            for (int t = ptid; t < 2 * CCH * NN * NA; t += PT_THR)   // never-copied rows are zero
+                if ((t / NA) % NN >= nn) Fp[t] = 0.f;
             uint64_t w2[KG][NN / 2];
             {
                 float R[9];
@@ -268,15 +307,39 @@ inter_fused_kernel(FusedParams P) {
                     }
                 }
             }
-            auto issue = [&](int chunk) {  // gather chunk `chunk` of this pass into buffer ci & 1
+            // Gather chunk `chunk` of this pass into buffer ci & 1: every thread of the point copies its share of the
+            // 16-byte pieces (15 per 240-byte feature row) with cp.async and then lets the buffer's mbarrier count
+            // its copies (arrive.noinc: the arrival fires when this thread's copies have landed).  One UBLKCP per
+            // row was issue-bound here: the copy instruction takes uniform registers, so a warp issues its lanes'
+            // copies one at a time (~1000 cycles per warp and chunk, measured).
+            auto issue = [&](int chunk) {
                 const int buf = ci & 1;
                 const uint32_t bar = gbar0 + 8u * (uint32_t)buf;
-                if (ptid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
-                for (int t = ptid; t < CCH * NN; t += PT_THR) {
-                    const int cl = t / NN, n = t % NN;
-                    if (n < nn)
-                        bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
-                                 F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA, ROW_BYTES, bar);
+                if (GATHER == 2) {
+                    constexpr int PIECES = CCH * NN * (NA / 4);
+#pragma unroll
+                    for (int it = 0; it < (PIECES + PT_THR - 1) / PT_THR; ++it) {
+                        const int t = ptid + it * PT_THR;
+                        const int piece = t % (NA / 4), slot = t / (NA / 4), cl = slot / NN, n = slot % NN;
+                        if (t < PIECES && n < nn) {
+                            const float *src = F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA + piece * 4;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                                         ::"r"(fs_u32 + (uint32_t)((((buf * CCH + cl) * NN + n) * NA + piece * 4) * 4)), "l"(src) : "memory");
+                        }
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+                } else {
+                    constexpr uint32_t ROW_BYTES = NA * 4;
+                    constexpr int SLOTS = CCH * NN;                       // 64 / 128 rows
+                    constexpr int SPREAD = GATHER == 1 ? PT_THR / SLOTS : 1;   // 3: every third thread owns a row
+                    if (ptid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
+                    const int t = ptid / SPREAD;
+                    if (ptid % SPREAD == 0 && t < SLOTS) {
+                        const int cl = t / NN, n = t % NN;
+                        if (n < nn)
+                            bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
+                                     F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA, ROW_BYTES, bar);
+                    }
                 }
                 ++ci;
             };
@@ -290,11 +353,11 @@ inter_fused_kernel(FusedParams P) {
                     const int chunk = g * CH_G + h;
                     const int cur = ci - 1;          // the chunk about to be consumed was issued last
                     const int buf = cur & 1;
-                    named_bar_sync(bar_id, NPROD);  // every thread of the point is done with the other gather buffer
+                    named_bar_sync(bar_id, NPROD);  // every producer thread is done with the other gather buffer
                     if (chunk + 1 < nchunks) issue(chunk + 1);
-                    mbar_wait(gbar0 + 8u * (uint32_t)buf, (uint32_t)(cur >> 1) & 1u);
+                    mbar_wait_q(gbar0 + 8u * (uint32_t)buf, (uint32_t)(cur >> 1) & 1u);
                     if (h == 0 && gi >= 2)  // the MMAs of granule gi-2 have read A[ab]
-                        mbar_wait(smem_u32(&s_afree[ab]), (uint32_t)((gi >> 1) - 1) & 1u);
+                        mbar_wait_q(afree0 + 8u * (uint32_t)ab, (uint32_t)((gi >> 1) - 1) & 1u);
                     const float *fbase = Fp + (size_t)(buf * CCH * NN) * NA + aa;
                     if (MODE == 1) {
                         // 4 channels x 6 kernel points = 24 values = K' chunks 12 g + 3 grp + {0,1,2}
@@ -389,7 +452,7 @@ inter_fused_kernel(FusedParams P) {
                 // granule complete: publish this warp's pieces to the tensor core
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&s_afull[ab]));
+                if (lane == 0) mbar_arrive(afull0 + 8u * (uint32_t)ab);
             }
         }
 
@@ -425,14 +488,21 @@ inter_fused_kernel(FusedParams P) {
     }
 }
 
-template <int MODE>
+template <int MODE, int GATHER>
 int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     using C = FuCfg<MODE>;
     constexpr int NPROD = C::PTS * FU_LANES * (FU_KS / C::KG);
     constexpr int ROWS = C::PTS * 64;
     constexpr size_t A_BYTES = (size_t)2 * (C::GCH * FU_KS / 32) * 2 * 4 * ROWS * 16 + (C::PTS == 1 ? 1024 : 0);
     const size_t fixed = A_BYTES + sizeof(float) * (size_t)C::PTS * 2 * FU_CCH * C::NN * FU_NA;
-    const size_t stage = (size_t)P.trb * 64;
+    // ring stage = sps 16-k steps (one bulk copy, one full/empty barrier round trip): the narrower the MMA (small
+    // c_out), the more steps per stage, so that the single control thread is not the bottleneck
+    P.sps = P.trb <= 64 ? 3 : (P.trb <= 128 ? 2 : 1);
+    if (const char *e = getenv("EPN_FU_SPS")) {   // tuning knob (tools/fused_sweep.py); must divide 6
+        const int v = atoi(e);
+        if (v == 1 || v == 2 || v == 3) P.sps = v;
+    }
+    const size_t stage = (size_t)P.trb * 64 * P.sps;
     const size_t budget = 227 * 1024 - 6 * 1024;  // static shared memory (neighbour lists, barriers) comes on top
     if (fixed + 2 * stage > budget) return 1;
     int nst = (int)((budget - fixed) / stage);
@@ -440,9 +510,9 @@ int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     P.nst = nst;
     const size_t smem_bytes = fixed + (size_t)nst * stage;
     static DynSmemOnce once;  // one per template instantiation
-    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE>, (int)budget, "inter_fused_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE, GATHER>, (int)budget, "inter_fused_kernel")) return rc;
     dim3 grid(p_cnt / C::PTS, bc);
-    inter_fused_kernel<MODE><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
+    inter_fused_kernel<MODE, GATHER><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
     return check_launch("inter_fused_kernel");
 }
 
@@ -482,8 +552,16 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
     while ((int)cols < P.trb) cols *= 2;
     P.tmem_cols = cols;
     ProfScope prof(s, KC_INTER_FUSED);
-    if (mode == 1) return launch_fused_variant<1>(P, p_cnt, bc, s);
-    return launch_fused_variant<2>(P, p_cnt, bc, s);
+    int gather = 1;
+    if (const char *e = getenv("EPN_FU_GATHER")) gather = atoi(e);   // tuning knob (tools/fused_sweep.py)
+    if (mode == 1) {
+        if (gather == 0) return launch_fused_variant<1, 0>(P, p_cnt, bc, s);
+        if (gather == 2) return launch_fused_variant<1, 2>(P, p_cnt, bc, s);
+        return launch_fused_variant<1, 1>(P, p_cnt, bc, s);
+    }
+    if (gather == 0) return launch_fused_variant<2, 0>(P, p_cnt, bc, s);
+    if (gather == 2) return launch_fused_variant<2, 2>(P, p_cnt, bc, s);
+    return launch_fused_variant<2, 1>(P, p_cnt, bc, s);
 }
 
 }  // namespace epn

@@ -102,7 +102,8 @@ int inter_group_direct_mode(const float *feats, int c, int nn, int na, int ks); 
 int launch_inter_group_direct(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, int k_blocks,
                               long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
                               int ks, cudaStream_t s);
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, cudaStream_t s);
+// steps = 1: the fused kernel's layout (every 16-k step contiguous, c_out <= 256) instead of split tiles
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s);
 // one input channel (feats NULL = occupancy ones), any row length up to 128: tiles of one K block in plain order
 bool inter_group_occ_ok(int c, int nn, int na, int ks);
 int launch_inter_group_occ(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, long long cols_per_z,

@@ -61,6 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Same bounded wait without the diagnostic printf (no call, no stack frame): for waits inside hot loops.
+__device__ __forceinline__ void mbar_wait_q(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (tensor core / bulk copy)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

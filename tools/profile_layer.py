@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--layer", type=int, default=3, help="0..6 = b0l0 .. b3l0")
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--iters", type=int, default=2)
+    ap.add_argument("--forward-only", action="store_true", help="inference forward under no_grad (fused inter kernel only)")
     args = ap.parse_args()
     layers = [l["args"] for blk in cls_backbone_params(1024, 60) for l in blk]
     a = layers[args.layer]
@@ -39,6 +40,10 @@ def main():
     xyz = (xyz / xyz.norm(dim=1, keepdim=True)).to(dev)
     feats = torch.randn(args.batch, a["dim_in"], p_in, 60, device=dev, requires_grad=True)
     for _ in range(args.iters):
+        if args.forward_only:
+            with torch.no_grad():
+                inter(E.SphericalPointCloud(xyz, feats, None))
+            continue
         _, _, _, y = inter(E.SphericalPointCloud(xyz, feats, None))
         z = intra(y)
         z.feats.square().mean().backward()
