@@ -138,6 +138,7 @@ class Workload:
         if self.name == "reg":
             from epn_pointcloud_b200 import functional as L, losses
             self._metric = losses.MultiTaskDetectionLoss(torch.from_numpy(L.get_anchors(60)).to(dev), nr=4)
+            self._metric.with_error = False   # the logging-only angular error needs an SVD (host sync): not part of the step
         return m
 
     def batch(self, n_items, seed):
@@ -460,8 +461,7 @@ def main():
         S = R.train_setup(wl, items, graph=False, warmup=args.warmup)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        if args.profile_forward:
-            S["model"].eval()
+        if args.profile_forward:   # same mode as the `forward` measurement: no_grad, module in training mode
             with torch.no_grad():
                 S["model"](S["x_dev"])
         else:

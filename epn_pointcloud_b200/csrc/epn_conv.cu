@@ -411,7 +411,7 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
     cudaStream_t s = as_stream(stream);
     // fused route: ONE kernel over every cloud, G stays in shared memory (its K' mode numbers are the direct kernels')
     int fused = 0;
-    if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && c_in > 1 && sp.pc == p)
+    if (gemm_backend() == 0 && fused_enabled() && feats != nullptr && c_in > 1 && (sp.pc == p || grouped == nullptr))
         fused = inter_fused_mode(c_in, c_out, p, nn, na, ks, grouped != nullptr);
     const int kperm = fused ? fused : inter_direct(feats, c_in, nn, na, ks);
     if (grouped != nullptr) {

@@ -138,6 +138,10 @@ class MultiTaskDetectionLoss(nn.Module):
         self.w = w
         self.threshold = threshold
         self.iter_counter = 0
+        # The last return value (mean angular error of the SO(3)-averaged prediction) is a logging metric; its SVD
+        # synchronises with the host.  with_error = False skips it (returns zeros) so that a training step can be
+        # captured into a CUDA graph; the loss terms are unaffected.
+        self.with_error = True
 
     def forward(self, wts, label, y, gt_R, gt_T=None):
         b, nr, na = wts.shape[0], self.nr, wts.shape[1]
@@ -158,7 +162,7 @@ class MultiTaskDetectionLoss(nn.Module):
             confidence = confidence / (1e-6 + confidence.sum(1, keepdim=True))
             src = self.anchors[None].expand(b, -1, -1, -1)
             pred_Rs = torch.einsum("baij,bajk,balk->bail", src, pred_res, self.anchors[preds])
-            pred_R = so3_mean(pred_Rs, confidence)
+            pred_R = so3_mean(pred_Rs, confidence) if self.with_error else true_R
             l2_loss = (gt_R - select_R).pow(2).mean()
             loss = cls_loss + self.w * l2_loss
         else:
@@ -208,14 +212,14 @@ class TripletBatchLoss(nn.Module):
 
     def forward(self, src, tgt, T, equi_src=None, equi_tgt=None):
         if self.alpha > 0 and equi_src is not None and equi_tgt is not None:
-            raise NotImplementedError("the equivariance term (alpha > 0, vgtk/vgtk/loss.py:320-358) is not mirrored")
+            return self._forward_equivariance(src, tgt, equi_src, equi_tgt, T)
         return self._forward_invariance(src, tgt)
 
-    def _forward_invariance(self, src, tgt):
-        n = src.shape[0]
-        all_dist = pairwise_distance_matrix(src, tgt)
-        pos = torch.diagonal(all_dist)
-        neg = batch_hard_negative_mining(all_dist)
+    def _triplet(self, dist):
+        """(loss, top-1 accuracy, mean positive distance, mean hardest-negative distance) of a distance matrix."""
+        n = dist.shape[0]
+        pos = torch.diagonal(dist)
+        neg = batch_hard_negative_mining(dist)
         diff = pos - neg
         if self.loss == "hard":
             diff = F.relu(diff + self.margin)
@@ -223,8 +227,39 @@ class TripletBatchLoss(nn.Module):
             diff = F.softplus(diff, beta=self.margin)
         elif self.loss == "contrastive":
             diff = pos + F.relu(self.margin - neg)
-        idx = torch.topk(all_dist, k=self.k_precision, dim=1, largest=False)[1]
+        idx = torch.topk(dist, k=self.k_precision, dim=1, largest=False)[1]
         gt = torch.arange(n, device=idx.device).view(n, 1).expand(-1, self.k_precision)
-        accuracy = (idx == gt).sum().float() / float(n)
+        return diff.mean(), (idx == gt).sum().float() / float(n), pos.mean(), neg.mean(), idx, pos, neg
+
+    def _forward_equivariance(self, src, tgt, equi_src, equi_tgt, T):
+        """Invariance loss + alpha * triplet loss between the per-anchor features of the source and the target
+        features carried into the source frame (vgtk/vgtk/loss.py:320-358) -> (total, inv_info, equi_info).
+        Upstream this branch raises for every batch size (the flattened neighbour index of _interpolate is reshaped as
+        if the batch were 1, loss.py:408-409, and a single sample has no negative to mine); this is the batched gather
+        its commented-out line describes, pinned against upstream's own single-sample _interpolate."""
+        inv_loss, acc, fp, cn = self._forward_invariance(src, tgt)
+        b = src.shape[0]
+        tgt_r = self._interpolate(equi_tgt, T, sigma=self.sigma).reshape(b, -1)
+        equi_loss, e_acc, e_fp, e_cn, _, _, _ = self._triplet(pairwise_distance_matrix(equi_src.reshape(b, -1), tgt_r))
+        return inv_loss + self.alpha * equi_loss, [inv_loss, acc, fp, cn], [equi_loss, e_acc, e_fp, e_cn]
+
+    def _rotation_distance(self, r0, r1, k=3):
+        """r0 [b,n,3,3], r1 [m,3,3] -> the k largest traces tr(r0 r1^T) and their indices, [b,n,k] (loss.py:430-433)"""
+        traces = torch.einsum("bnij,mij->bnm", r0, r1)
+        return traces.topk(k=k, dim=2)
+
+    def _interpolate(self, feature, T, knn=3, sigma=1e-1):
+        """feature [b, c, na] rotated by T [b, 3(4), 3(4)]: every anchor takes the softmax(trace / sigma)-weighted mean
+        of the features at the knn anchors closest to R^T anchor (loss.py:390-428) -> [b, c, na]."""
+        b, c, na = feature.shape
+        r_anchors = torch.einsum("bij,njk->bnik", T[:, :3, :3].transpose(1, 2), self.anchors)
+        infl, idx = self._rotation_distance(r_anchors, self.anchors, k=knn)
+        infl = F.softmax(infl / sigma, 2)[:, None]                                   # [b, 1, na, k]
+        feat = torch.gather(feature, 2, idx.reshape(b, 1, na * knn).expand(-1, c, -1)).view(b, c, na, knn)
+        return (feat * infl).sum(-1)
+
+    def _forward_invariance(self, src, tgt):
+        all_dist = pairwise_distance_matrix(src, tgt)
+        loss, accuracy, fpos, cneg, idx, pos, neg = self._triplet(all_dist)
         self.match_idx, self.all_dist, self.fpos, self.cneg = idx, all_dist, pos, neg
-        return diff.mean(), accuracy, pos.mean(), neg.mean()
+        return loss, accuracy, fpos, cneg

@@ -77,6 +77,14 @@ def main():
         opt = types.SimpleNamespace(device="cpu", train_loss=types.SimpleNamespace(loss_type=lt, margin=1.0))
         res = RL.TripletBatchLoss(opt, anchors)(src, tgt, None)
         out["tri_" + lt] = np.array([float(v) for v in res], dtype=np.float64)
+    # the rotated-feature interpolation of the equivariance term: upstream's _interpolate only runs for ONE sample
+    # (its flattened index is reshaped as if the batch were 1, vgtk/vgtk/loss.py:408-409), so three single-sample calls
+    opt = types.SimpleNamespace(device="cpu", train_loss=types.SimpleNamespace(loss_type="soft", margin=1.0))
+    tl = RL.TripletBatchLoss(opt, anchors, alpha=0.5)
+    feat = torch.randn(3, 8, 60, generator=g)
+    Ts = RF.compute_rotation_matrix_from_quaternion(torch.randn(3, 4, generator=g))
+    outs = [tl._interpolate(feat[i:i + 1], Ts[i:i + 1], sigma=0.2) for i in range(3)]
+    out.update(interp_feat=npy(feat), interp_T=npy(Ts), interp_out=npy(torch.cat(outs, 0)))
     save("losses", **out)
 
 

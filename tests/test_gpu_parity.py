@@ -321,6 +321,7 @@ def test_backbone_small_vs_golden(E):
     for k, key in names.items():
         truth = leaves[key].grad
         e_mine, e_ref = frob(dict(model.named_parameters())[k].grad, truth), frob(grads[k], truth)
+        print("chained grad %s: engine %.2e, reference fp32 %.2e (from fp64)" % (k, e_mine, e_ref))
         assert e_ref < 1e-3 and e_mine < 3e-2, (k, e_mine, e_ref)
 
 
@@ -745,6 +746,7 @@ def test_inv_model_vs_reference_golden(E):
     with torch.no_grad():
         desc, attn = model(g["pc"].to(DEV))
     assert desc.shape == g["desc"].shape and attn.shape == g["attn"].shape
+    print("inv model golden: desc %.2e attn %.2e" % (rel_err(desc, g["desc"]), rel_err(attn, g["attn"])))
     assert rel_err(desc, g["desc"]) < 2e-4 and rel_err(attn, g["attn"]) < 2e-4
 
 
@@ -758,6 +760,7 @@ def test_reg_model_vs_reference_golden(E):
     with torch.no_grad():
         conf, quats = model(g["pairs"].to(DEV))
     assert conf.shape == g["conf"].shape and quats.shape == g["quats"].shape
+    print("reg model golden: conf %.2e quats %.2e" % (rel_err(conf, g["conf"]), rel_err(quats, g["quats"])))
     assert rel_err(conf, g["conf"]) < 2e-4 and rel_err(quats, g["quats"]) < 2e-4
 
 

@@ -75,5 +75,29 @@ def test_triplet_batch_loss(g, loss_type):
     assert np.allclose(got, g["tri_" + loss_type].numpy(), rtol=1e-6, atol=1e-7)
     d = LS.pairwise_distance_matrix(g["tri_src"], g["tri_tgt"])
     assert torch.allclose(d, torch.cdist(g["tri_src"], g["tri_tgt"]), atol=1e-5)
-    with pytest.raises(NotImplementedError):
-        LS.TripletBatchLoss(opt, torch.eye(3)[None], alpha=0.5)(g["tri_src"], g["tri_tgt"], None, g["tri_src"], g["tri_tgt"])
+
+
+def test_triplet_equivariance_term(g):
+    """alpha > 0 (vgtk/vgtk/loss.py:320-428).  Upstream's branch raises for every batch size, so the pins are its own
+    single-sample `_interpolate` outputs (golden), the identity-rotation property and the composition of the two
+    triplet terms."""
+    from epn_pointcloud_b200 import functional as L
+    anchors = torch.from_numpy(L.get_anchors(60))
+    opt = types.SimpleNamespace(device="cpu", train_loss=types.SimpleNamespace(loss_type="soft", margin=1.0))
+    m = LS.TripletBatchLoss(opt, anchors, alpha=0.5)
+    # batched interpolation == upstream's per-sample results
+    assert rel_err(m._interpolate(g["interp_feat"], g["interp_T"], sigma=0.2), g["interp_out"]) < 1e-5
+    # identity rotation with a sharp kernel returns the features themselves
+    eye = torch.eye(3)[None].repeat(3, 1, 1)
+    assert rel_err(m._interpolate(g["interp_feat"], eye, sigma=1e-3), g["interp_feat"]) < 1e-5
+    # total = invariance + alpha * triplet(equi_src, interpolated equi_tgt)
+    src, tgt = g["tri_src"][:3], g["tri_tgt"][:3]
+    es = g["interp_feat"]
+    et = es + 0.05 * torch.randn(es.shape, generator=torch.Generator().manual_seed(3))
+    total, inv_info, equi_info = m(src, tgt, eye, es, et)
+    inv = LS.TripletBatchLoss(opt, anchors)(src, tgt, None)
+    assert abs(float(inv_info[0]) - float(inv[0])) < 1e-7
+    d = LS.pairwise_distance_matrix(es.reshape(3, -1), m._interpolate(et, eye, sigma=m.sigma).reshape(3, -1))
+    want = torch.nn.functional.softplus(torch.diagonal(d) - LS.batch_hard_negative_mining(d), beta=1.0).mean()
+    assert abs(float(equi_info[0]) - float(want)) < 1e-6 and abs(float(total) - float(inv[0]) - 0.5 * float(want)) < 1e-6
+    assert float(equi_info[1]) == 1.0   # matching anchors' features retrieve each other
