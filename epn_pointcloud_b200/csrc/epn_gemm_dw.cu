@@ -7,11 +7,21 @@
 // For dW the contraction runs over n, so G enters as the M operand (M = kk) and n is the MMA K dimension.
 // Read that way the very same bytes are the canonical MN-MAJOR no-swizzle layout of tcgen05: 8 kk contiguous
 // (16 bytes), consecutive n 16 bytes apart, i.e. one 8(k) x 8(mn) core matrix = 128 contiguous bytes.  So the
-// backward pass neither recomputes the spatial contraction nor transposes anything: the producer copies
+// backward pass neither recomputes the spatial contraction nor transposes anything: the producer moves the
 // 1-KB pieces (64 n of one 8-kk group) of four adjacent forward tiles into a stage
 //     A stage = [part][kk group: 16][n: 64][8 kk]     SBO (8-kk group stride) = 1 KB, LBO (8-n group stride) = 128 B
 // and the MMA is issued with a_major = MN.  B = dout tiles (rows = o, K = n), K-major as everywhere else.
+//
+// The tile array is a dense 4-D tensor of 32-bit words  [k-block (over all row tiles)][part 2][k-chunk 4][512]
+// (strides 16 KB / 8 KB / 2 KB / 4 B; the 128 rows x 16 B of one k-chunk are 2 KB contiguous), so ONE tensor-map
+// TMA load (box 4 x 1 x 4 x 256 words = 16 KB, inner extent 1 KB) brings the 16 pieces of one part of a stage; two
+// loads + the two dout tiles make a stage.  (A 5-D map with the 16-byte rows as the inner dimension was measured
+// SLOWER than the bulk copies: the TMA unit works in units of the box's inner extent.)  (The first version issued the
+// 32 pieces as 32 bulk copies: a warp issues those one lane at a time, ~26 GB/s per issuing warp, and the kernel
+// ran at 3.3 TB/s; epn_set/EPN_DW_TMA=0 selects that path for comparison.)
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
@@ -34,7 +44,8 @@ struct DwParams {
     int ck, c_out, kperm;
 };
 
-__global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
+template <bool TMA>
+__global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_constant__ CUtensorMap g_map) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (p.units + p.split_k - 1) / p.split_k;
@@ -82,17 +93,28 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
         const uint32_t a_dst = (uint32_t)part * A_PART + (uint32_t)(j * 4 + kc) * (UNIT * 16);
         const size_t a_off = (size_t)kb * tile_bytes(TR_A) + (size_t)part * part_bytes(TR_A) + (size_t)kc * (TR_A * 16);
         const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.b_k_blocks) * b_tile;
+        if (TMA && warp == 0 && lane == 0) tma_prefetch_desc(&g_map);
         for (int i = warp; i < nu && warp < NPW; i += NPW) {
             const int s = i % p.stages;
             const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
             const int u = u0 + i;
             mbar_wait(empty_bar(s), ph ^ 1u);
-            if (lane == 0) mbar_arrive_expect_tx(full_bar(s), tx);
-            __syncwarp();
             const uint32_t st = base + s * stage_bytes;
-            if (has)
-                bulk_g2s(st + a_dst, p.G + (size_t)(u >> 1) * p.g_k_blocks * tile_bytes(TR_A) + a_off + (size_t)(u & 1) * (UNIT * 16),
-                         UNIT * 16, full_bar(s));
+            if (TMA) {
+                // k-blocks past the end of this row tile's K range (ck not a multiple of 128) come from the next row
+                // tile or are zero-filled: they only feed dW^T rows >= ck, which the epilogue drops
+                if (lane == 0) mbar_arrive_expect_tx(full_bar(s), A_STAGE + 2 * b_tile);
+                __syncwarp();
+                if (lane < 2)
+                    tma_load_4d(st + lane * A_PART, &g_map, full_bar(s), (u & 1) * (UNIT * 4), 0, lane,
+                                (u >> 1) * p.g_k_blocks + 4 * (int)blockIdx.x);
+            } else {
+                if (lane == 0) mbar_arrive_expect_tx(full_bar(s), tx);
+                __syncwarp();
+                if (has)
+                    bulk_g2s(st + a_dst, p.G + (size_t)(u >> 1) * p.g_k_blocks * tile_bytes(TR_A) + a_off + (size_t)(u & 1) * (UNIT * 16),
+                             UNIT * 16, full_bar(s));
+            }
             if (lane < 2)
                 bulk_g2s(st + A_STAGE + lane * b_tile, b_src + (size_t)(2 * u + lane) * b_tile, b_tile, full_bar(s));
         }
@@ -147,6 +169,30 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p) {
     }
 }
 
+// Tensor map over the forward tile array (see the header comment): dims innermost first.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_tile_map(CUtensorMap *map, const void *tiles, unsigned long long n_kblocks_total) {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    if (fn == nullptr) return 1;
+    const cuuint64_t dims[4] = {512, 4, 2, n_kblocks_total};     // 32-bit words
+    const cuuint64_t strides[3] = {2048, 8192, 16384};            // bytes, dims 1..3
+    const cuuint32_t box[4] = {(cuuint32_t)UNIT * 4, 4, 1, 4};    // 64 rows x 16 B = 256 words
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(tiles), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 1;
+}
+
 }  // namespace
 
 // G_tiles: forward operand tiles of one slab (n rows, n % 128 == 0, K = ck); B_tiles: dout tiles (rows = c_out, K = n)
@@ -156,8 +202,9 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
         set_error("umma_dw: n must be a multiple of 128");
         return EPN_ERR_SHAPE;
     }
-    static DynSmemOnce once;
-    if (int rc = ensure_dyn_smem(once, umma_dw_kernel, 220 * 1024, "umma_dw_kernel")) return rc;
+    static DynSmemOnce once, once_tma;
+    if (int rc = ensure_dyn_smem(once, umma_dw_kernel<false>, 220 * 1024, "umma_dw_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once_tma, umma_dw_kernel<true>, 220 * 1024, "umma_dw_kernel")) return rc;
     DwParams p;
     p.G = static_cast<const uint8_t *>(G_tiles);
     p.B = static_cast<const uint8_t *>(B_tiles);
@@ -192,7 +239,14 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
     dim3 grid(m_tiles, n_tiles, (unsigned)sk);
     const size_t smem = (size_t)stages * stage + 128 + 16 * stages + 32;
     ProfScope prof(s, KC_GEMM);
-    umma_dw_kernel<<<grid, 192, smem, s>>>(p);
+    static const int use_tma = (getenv("EPN_DW_TMA") && atoi(getenv("EPN_DW_TMA")) == 0) ? 0 : 1;
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (use_tma && encode_tile_map(&map, G_tiles, (unsigned long long)(n / TR_A) * p.g_k_blocks) == 0) {
+        umma_dw_kernel<true><<<grid, 192, smem, s>>>(p, map);
+    } else {
+        umma_dw_kernel<false><<<grid, 192, smem, s>>>(p, map);
+    }
     return check_launch("umma_dw_kernel");
 }
 
