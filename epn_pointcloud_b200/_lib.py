@@ -96,7 +96,7 @@ SIGNATURES = {
     "epn_basic_conv_fwd_f32": (c_i, [c_f] * 4 + [c_sz] + [c_i] * 4 + [c_f]),
     "epn_basic_conv_bwd_f32": (c_i, [c_f] * 6 + [c_sz] + [c_i] * 4 + [c_f]),
     "epn_norm_act_workspace_bytes": (c_sz, [c_i, c_i]),
-    "epn_norm_act_fwd_f32": (c_i, [c_f] * 6 + [c_sz] + [c_i] * 4 + [c_fl, c_fl, c_f]),
+    "epn_norm_act_fwd_f32": (c_i, [c_f] * 7 + [c_sz] + [c_i] * 4 + [c_fl, c_fl, c_f]),
     "epn_norm_act_bwd_f32": (c_i, [c_f] * 9 + [c_sz] + [c_i] * 4 + [c_fl, c_f]),
     "epn_set_gemm_backend": (None, [c_i]),
     "epn_set_slab_bytes": (None, [c_sz]),

@@ -15,12 +15,17 @@ from . import ops
 
 
 class _NormActFn(torch.autograd.Function):
-    """leaky_relu(norm(x)) as one library op (epn_norm_act_*); saves x and the (mean, rstd) statistics."""
+    """leaky_relu(norm(x)) [+ residual] as one library op (epn_norm_act_*); saves x and the (mean, rstd) statistics."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, mode, eps, slope):
+    def forward(ctx, x, gamma, beta, mode, eps, slope, residual=None, cancelled_bias=None):
+        # cancelled_bias: a per-channel constant added to x upstream (the skip convolution's bias).  The normalisation
+        # removes it again, so it is never added; it only takes part in autograd, where its exact gradient is zero.
+        ctx.bias_shape = None if cancelled_bias is None else cancelled_bias.shape
         x = x.contiguous()
-        y, stats = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope)
+        if residual is not None:
+            residual = residual.contiguous()
+        y, stats = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope, residual)
         ctx.save_for_backward(x, stats, gamma, beta)
         ctx.mode, ctx.slope = mode, slope
         ctx.mark_non_differentiable(stats)
@@ -29,35 +34,46 @@ class _NormActFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, _dstats):
         x, stats, gamma, beta = ctx.saved_tensors
-        dx, dgamma, dbeta = ops.norm_act_bwd(dy.contiguous(), x, gamma, beta, stats, ctx.mode, ctx.slope)
-        return dx, dgamma, dbeta, None, None, None
+        dy = dy.contiguous()
+        dx, dgamma, dbeta = ops.norm_act_bwd(dy, x, gamma, beta, stats, ctx.mode, ctx.slope)
+        dbias = dy.new_zeros(ctx.bias_shape) if (ctx.bias_shape is not None and ctx.needs_input_grad[7]) else None
+        return dx, dgamma, dbeta, None, None, None, (dy if ctx.needs_input_grad[6] else None), dbias
 
 
-def norm_act(norm, x, act):
-    """`act(norm(x))` of the block wrappers (base_so3conv.py:55-57,119-125,209).  The two combinations every
-    shipped model uses on CUDA -- InstanceNorm2d(affine=False) / training-mode BatchNorm2d followed by
-    leaky_relu -- run as one fused library op; anything else goes through the torch modules."""
+def norm_act(norm, x, act, residual=None, bias=None):
+    """`act(norm(x + bias)) + residual` of the block wrappers (base_so3conv.py:55-57,119-125,209-211).  The two
+    combinations every shipped model uses on CUDA -- InstanceNorm2d(affine=False) / training-mode BatchNorm2d followed
+    by leaky_relu -- run as one fused library op; anything else goes through the torch modules.
+
+    `bias` [c] is the bias of the 1x1 skip convolution that produced x.  A normalisation with statistics of x itself
+    subtracts the per-channel mean, so a per-channel constant cancels exactly: the fused paths never add it (one
+    full pass over the tensor saved; its gradient is identically zero) and only fold it into BatchNorm's running
+    mean, which does see it."""
     fusable = x.is_cuda and x.dtype == torch.float32 and act is F.leaky_relu and x.dim() == 4
     if fusable and isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats:
-        return _NormActFn.apply(x, None, None, 0, norm.eps, 0.01)[0]
+        return _NormActFn.apply(x, None, None, 0, norm.eps, 0.01, residual, bias)[0]
     if fusable and isinstance(norm, nn.BatchNorm2d) and norm.training and norm.affine:
-        y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, 0.01)
+        y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, 0.01, residual, bias)
         if norm.track_running_stats:  # same bookkeeping as nn.BatchNorm2d.forward
             with torch.no_grad():
                 count = x.numel() // x.shape[1]
                 norm.num_batches_tracked += 1
+                mean = stats[0] if bias is None else stats[0] + bias.detach()
                 var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))
                 if norm.momentum is not None:
                     m = norm.momentum
-                    norm.running_mean.mul_(1 - m).add_(stats[0], alpha=m)
+                    norm.running_mean.mul_(1 - m).add_(mean, alpha=m)
                     norm.running_var.mul_(1 - m).add_(var, alpha=m)
                 else:  # cumulative moving average: the factor stays on the device (no host sync, graph-capturable)
                     m = 1.0 / norm.num_batches_tracked.to(torch.float32)
-                    norm.running_mean.add_((stats[0] - norm.running_mean) * m)
+                    norm.running_mean.add_((mean - norm.running_mean) * m)
                     norm.running_var.add_((var - norm.running_var) * m)
         return y
+    if bias is not None:
+        x = x + bias.view(1, -1, 1, 1)
     out = norm(x)
-    return act(out) if act is not None else out
+    out = act(out) if act is not None else out
+    return out if residual is None else out + residual
 
 
 def preprocess_input(x, na, add_center=True):
@@ -144,13 +160,17 @@ class SeparableSO3ConvBlock(nn.Module):
         if self.use_intra:
             x = self.intra_conv(x)
         if self.stride > 1:
-            skip_feature = L.batched_index_select(skip_feature, 2, sample_idx.long())
+            if self.inter_conv.conv.lazy_sample:   # prefix sampling (pc/sample.py:64-67): the gather is a slice
+                skip_feature = skip_feature[:, :, :sample_idx.shape[1]]
+            else:
+                skip_feature = L.batched_index_select(skip_feature, 2, sample_idx.long())
         # 1x1 skip conv = a BasicSO3Conv with kernel size 1: run it through the library's fp32-faithful
         # channel GEMM (cuDNN would silently use TF32), parameters stay in nn.Conv2d for checkpoint parity
         w = self.skip_conv.weight.view(self.skip_conv.out_channels, self.skip_conv.in_channels)
-        skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w) + self.skip_conv.bias.view(1, -1, 1, 1)
-        skip_feature = norm_act(self.norm, skip_feature, self.relu)
-        x_out = sptk.SphericalPointCloud(x.xyz, x.feats + skip_feature, x.anchors)
+        skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w)
+        # bias add, normalisation, activation and the residual add in one pass (see norm_act)
+        feats = norm_act(self.norm, skip_feature, self.relu, residual=x.feats, bias=self.skip_conv.bias)
+        x_out = sptk.SphericalPointCloud(x.xyz, feats, x.anchors)
         return inter_idx, inter_w, sample_idx, x_out
 
     def get_anchor(self):

@@ -83,7 +83,8 @@ __device__ __forceinline__ float lrelu(float z, float slope) { return z > 0.f ? 
 
 __global__ void __launch_bounds__(NT)
 norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, const float *__restrict__ beta,
-                  const float *__restrict__ stats, float *__restrict__ y, int c, int n, int G, int mode, float slope) {
+                  const float *__restrict__ stats, const float *__restrict__ residual, float *__restrict__ y, int c, int n,
+                  int G, int mode, float slope) {
     const int rowi = blockIdx.y;
     const int ch = rowi % c;
     const int gi = mode == 0 ? rowi : ch;
@@ -91,6 +92,7 @@ norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, 
     const float ga = gamma ? gamma[ch] : 1.f, be = beta ? beta[ch] : 0.f;
     const float sc = rstd * ga, sh = be - mean * sc;
     const float *row = x + (size_t)rowi * n;
+    const float *res = residual ? residual + (size_t)rowi * n : nullptr;   // skip connection: y = act(norm(x)) + residual
     float *out = y + (size_t)rowi * n;
     if (n % 4 == 0) {
         for (int i = blockIdx.x * NT + threadIdx.x; i < n / 4; i += gridDim.x * NT) {
@@ -100,10 +102,15 @@ norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, 
             r.y = lrelu(fmaf(v.y, sc, sh), slope);
             r.z = lrelu(fmaf(v.z, sc, sh), slope);
             r.w = lrelu(fmaf(v.w, sc, sh), slope);
+            if (res != nullptr) {
+                const float4 q = __ldg(reinterpret_cast<const float4 *>(res) + i);
+                r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
+            }
             reinterpret_cast<float4 *>(out)[i] = r;
         }
     } else {
-        for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) out[i] = lrelu(fmaf(row[i], sc, sh), slope);
+        for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT)
+            out[i] = lrelu(fmaf(row[i], sc, sh), slope) + (res ? res[i] : 0.f);
     }
 }
 
@@ -120,13 +127,19 @@ norm_bwd_reduce_kernel(const float *__restrict__ dy, const float *__restrict__ x
     const float ga = gamma ? gamma[ch] : 1.f, be = beta ? beta[ch] : 0.f;
     const float *xr = x + (size_t)rowi * n, *dr = dy + (size_t)rowi * n;
     float s1 = 0.f, s2 = 0.f;
-    for (int i = threadIdx.x; i < n; i += NT) {
-        const float xh = (__ldg(xr + i) - mean) * rstd;
+    auto term = [&](float xv, float dv) {
+        const float xh = (xv - mean) * rstd;
         const float z = fmaf(xh, ga, be);
-        const float gd = __ldg(dr + i) * (z > 0.f ? 1.f : slope);
+        const float gd = dv * (z > 0.f ? 1.f : slope);
         s1 += gd;
         s2 = fmaf(gd, xh, s2);
+    };
+    const int n4 = (n % 4 == 0 && (((uintptr_t)xr | (uintptr_t)dr) & 15) == 0) ? n / 4 : 0;
+    for (int i = threadIdx.x; i < n4; i += NT) {
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr) + i), dv = __ldg(reinterpret_cast<const float4 *>(dr) + i);
+        term(xv.x, dv.x); term(xv.y, dv.y); term(xv.z, dv.z); term(xv.w, dv.w);
     }
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += NT) term(__ldg(xr + i), __ldg(dr + i));
     s1 = block_sum(s1, s_red);
     s2 = block_sum(s2, s_red);
     if (threadIdx.x == 0) part[rowi] = make_float2(s1, s2);
@@ -161,12 +174,18 @@ norm_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     const float m1 = sm.x * inv_count, m2 = sm.y * inv_count, k = ga * rstd;
     const float *xr = x + (size_t)rowi * n, *dr = dy + (size_t)rowi * n;
     float *out = dx + (size_t)rowi * n;
-    for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) {
-        const float xh = (__ldg(xr + i) - mean) * rstd;
+    auto elem = [&](float xv, float dv) {
+        const float xh = (xv - mean) * rstd;
         const float z = fmaf(xh, ga, be);
-        const float gd = __ldg(dr + i) * (z > 0.f ? 1.f : slope);
-        out[i] = k * (gd - m1 - xh * m2);
+        const float gd = dv * (z > 0.f ? 1.f : slope);
+        return k * (gd - m1 - xh * m2);
+    };
+    const int n4 = (n % 4 == 0 && (((uintptr_t)xr | (uintptr_t)dr | (uintptr_t)out) & 15) == 0) ? n / 4 : 0;
+    for (int i = blockIdx.x * NT + threadIdx.x; i < n4; i += gridDim.x * NT) {
+        const float4 xv = __ldg(reinterpret_cast<const float4 *>(xr) + i), dv = __ldg(reinterpret_cast<const float4 *>(dr) + i);
+        reinterpret_cast<float4 *>(out)[i] = make_float4(elem(xv.x, dv.x), elem(xv.y, dv.y), elem(xv.z, dv.z), elem(xv.w, dv.w));
     }
+    for (int i = n4 * 4 + blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) out[i] = elem(__ldg(xr + i), __ldg(dr + i));
 }
 
 }  // namespace epn
@@ -178,15 +197,15 @@ EPN_API size_t epn_norm_act_workspace_bytes(int b, int c) {
     return (size_t)2 * b * c * sizeof(float2) + 256;
 }
 
-EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, float *y, float *stats,
-                                 void *workspace, size_t workspace_bytes, int b, int c, int n, int mode, float eps,
-                                 float slope, void *stream) {
+EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, const float *residual, float *y,
+                                 float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n, int mode,
+                                 float eps, float slope, void *stream) {
     EPN_REQUIRE_PTR(x); EPN_REQUIRE_PTR(y); EPN_REQUIRE_PTR(stats); EPN_REQUIRE_PTR(workspace);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c); EPN_REQUIRE_POS(n);
     EPN_REQUIRE(mode == 0 || mode == 1, EPN_ERR_SHAPE, "mode must be 0 (instance) or 1 (batch)");
     EPN_REQUIRE((long long)b * c <= 2147483647LL / 2, EPN_ERR_SHAPE, "b*c too large");
     EPN_REQUIRE(workspace_bytes >= epn_norm_act_workspace_bytes(b, c), EPN_ERR_WORKSPACE, "workspace too small");
-    EPN_REQUIRE((((uintptr_t)x | (uintptr_t)y) & 15) == 0, EPN_ERR_ALIGN, "x and y must be 16-byte aligned");
+    EPN_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) == 0, EPN_ERR_ALIGN, "x, y and residual must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
     float2 *part = static_cast<float2 *>(workspace);
     const int rows = b * c, G = mode == 0 ? rows : c;
@@ -202,7 +221,7 @@ EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float
         set_error("epn_norm_act_fwd_f32: b*c = %d rows exceed the grid limit", rows);
         return EPN_ERR_SHAPE;
     }
-    norm_apply_kernel<<<grid, NT, 0, s>>>(x, gamma, beta, stats, y, c, n, G, mode, slope);
+    norm_apply_kernel<<<grid, NT, 0, s>>>(x, gamma, beta, stats, residual, y, c, n, G, mode, slope);
     return check_launch("norm_apply_kernel");
 }
 
@@ -232,7 +251,7 @@ EPN_API int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *g
         if (rc) return rc;
         group_sums = sums;
     }
-    dim3 grid(cdiv(n, NT * 8) > 0 ? cdiv(n, NT * 8) : 1, rows);
+    dim3 grid(cdiv(n, NT * 4 * 4) > 0 ? cdiv(n, NT * 4 * 4) : 1, rows);
     const float inv_count = mode == 0 ? 1.0f / (float)n : 1.0f / ((float)b * (float)n);
     norm_bwd_apply_kernel<<<grid, NT, 0, s>>>(dy, x, gamma, beta, stats, group_sums, dx, c, n, G, mode, slope, inv_count);
     return check_launch("norm_bwd_apply_kernel");

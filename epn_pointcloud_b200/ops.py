@@ -433,10 +433,11 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True,
     return dfeats, dW
 
 
-def norm_act_fwd(x, gamma, beta, mode, eps, slope):
+def norm_act_fwd(x, gamma, beta, mode, eps, slope, residual=None):
     """x [b,c,p,a] -> (y, stats[2,G]); mode 0 = InstanceNorm2d(affine=False), 1 = BatchNorm2d (batch statistics),
-    followed by leaky_relu(slope)  (SPConvNets/utils/base_so3conv.py:43,55-57,107,119-125)."""
-    _require_cuda(x, gamma, beta)
+    followed by leaky_relu(slope)  (SPConvNets/utils/base_so3conv.py:43,55-57,107,119-125); `residual` (same shape)
+    is added to the result in the same pass (the skip connection, base_so3conv.py:209-211)."""
+    _require_cuda(x, gamma, beta, residual)
     b, c = x.shape[0], x.shape[1]
     n = x[0, 0].numel()
     y = torch.empty_like(x)
@@ -445,7 +446,7 @@ def norm_act_fwd(x, gamma, beta, mode, eps, slope):
     with torch.cuda.device(x.device):
         wsb = L.epn_norm_act_workspace_bytes(b, c)
         ws = _workspace(wsb, x.device)
-        _lib.check(L.epn_norm_act_fwd_f32(_p(x), _p(gamma), _p(beta), _p(y), _p(stats), _p(ws), wsb, b, c, n, int(mode),
+        _lib.check(L.epn_norm_act_fwd_f32(_p(x), _p(gamma), _p(beta), _p(residual), _p(y), _p(stats), _p(ws), wsb, b, c, n, int(mode),
                                           float(eps), float(slope), _stream()), "epn_norm_act_fwd_f32")
     return y, stats
 

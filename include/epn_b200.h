@@ -211,12 +211,14 @@ int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, fl
  *   mode 1: BatchNorm2d, batch statistics, affine -> leaky_relu  (base_so3conv.py:107,119-125,193,209)
  * gamma/beta [c] may be NULL (= 1 / 0).  stats [2*G] receives (mean, rstd) per group, G = b*c (mode 0)
  * or c (mode 1); the backward needs it, and the caller derives BatchNorm's running statistics from it.
+ * residual [b, c, n] (NULL = none): the skip connection of SeparableSO3ConvBlock fused into the same pass,
+ *   y = leaky_relu(...) + residual   (base_so3conv.py:209-211); its gradient is dy itself.
  * Backward writes dx fully and, for mode 1, dgamma/dbeta [c] (NULL to skip).
  * workspace: epn_norm_act_workspace_bytes(b, c) bytes. */
 size_t epn_norm_act_workspace_bytes(int b, int c);
-int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, float *y, float *stats,
-                         void *workspace, size_t workspace_bytes, int b, int c, int n, int mode, float eps,
-                         float slope, void *stream);
+int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, const float *residual, float *y,
+                         float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n, int mode,
+                         float eps, float slope, void *stream);
 int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *gamma, const float *beta,
                          const float *stats, float *dx, float *dgamma, float *dbeta, void *workspace,
                          size_t workspace_bytes, int b, int c, int n, int mode, float slope, void *stream);

@@ -702,6 +702,41 @@ def test_fused_norm_act_vs_torch_fp64(E, b, c, p, a):
             assert int(mine.num_batches_tracked) == 1
 
 
+@pytest.mark.parametrize("kind", ["batch", "instance"])
+def test_fused_norm_act_with_skip_bias_and_residual(E, kind):
+    """The skip branch of SeparableSO3ConvBlock (base_so3conv.py:206-211): act(norm(conv(x) + bias)) + residual in ONE
+    pass.  The per-channel bias cancels in the normalisation, so the kernel never adds it: outputs, the gradients of
+    x and of the residual, and BatchNorm's running mean (which does see the bias) against torch in float64."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from epn_pointcloud_b200.blocks import norm_act
+    b, c, p, a = 3, 8, 16, 60
+    gen = torch.Generator().manual_seed(77)
+    x0 = torch.randn(b, c, p, a, generator=gen) * 2.0 + 1.0
+    res0 = torch.randn(b, c, p, a, generator=gen)
+    bias0 = torch.randn(c, generator=gen) * 3.0
+    r = torch.randn(b, c, p, a, generator=gen)
+    if kind == "batch":
+        mine, ref = nn.BatchNorm2d(c).to(DEV).train(), nn.BatchNorm2d(c).double().train()
+    else:
+        mine, ref = nn.InstanceNorm2d(c, affine=False).to(DEV), nn.InstanceNorm2d(c, affine=False).double()
+    xg, rg = x0.to(DEV).requires_grad_(True), res0.to(DEV).requires_grad_(True)
+    bg = bias0.to(DEV).requires_grad_(True)
+    xr, rr, br = x0.double().requires_grad_(True), res0.double().requires_grad_(True), bias0.double().requires_grad_(True)
+    y = norm_act(mine, xg, F.leaky_relu, residual=rg, bias=bg)
+    zr = ref(xr + br.view(1, -1, 1, 1))
+    yr = F.leaky_relu(zr) + rr
+    assert rel_err(y, yr) < 1e-5
+    (y * r.to(DEV)).sum().backward()
+    (yr * r.double()).sum().backward()
+    keep = (zr.detach().abs() > 1e-5 * zr.detach().abs().max()).to(DEV)
+    assert rel_err(xg.grad * keep, xr.grad * keep.cpu()) < 1e-4
+    assert torch.equal(rg.grad.cpu(), r)                      # the residual's gradient is dy itself
+    assert float(bg.grad.abs().max()) == 0.0 and float(br.grad.abs().max()) < 1e-9 * float(r.abs().sum())   # exactly zero
+    if kind == "batch":
+        assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-4
+
+
 # ------------------------------------------------------------ classification head + full model (8 f2)
 def test_cls_head_vs_golden(E):
     """ClsOutBlockPointnet + PointnetSO3Conv (base_so3conv.py:358-448, so3conv/modules.py:203-235) against
