@@ -63,23 +63,18 @@ inter_group_direct_kernel(const float *__restrict__ feats, const int32_t *__rest
         float R[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
+        const float inv_sigma = 1.0f / g.sigma;
+        const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
 #pragma unroll
         for (int i = 0; i < KG; ++i) {
             const float kx = __ldg(g.kernels + (k0 + i) * 3), ky = __ldg(g.kernels + (k0 + i) * 3 + 1),
                         kz = __ldg(g.kernels + (k0 + i) * 3 + 2);
-            const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
-                        rz = R[6] * kx + R[7] * ky + R[8] * kz;
+            const KPoint2 rk = kpoint2(R[0] * kx + R[1] * ky + R[2] * kz, R[3] * kx + R[4] * ky + R[5] * kz,
+                                       R[6] * kx + R[7] * ky + R[8] * kz);
 #pragma unroll
-            for (int n = 0; n < NN; n += 2) {
-                float v[2];
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const float t = kernel_weight_fast(s_g[(n + e) * 3], s_g[(n + e) * 3 + 1], s_g[(n + e) * 3 + 2], rx, ry, rz,
-                                                       1.0f / g.sigma);
-                    v[e] = (a_ok && n + e < nn) ? t * s_mult[n + e] : 0.f;
-                }
-                w2[i][n / 2] = pack_f32x2(v[0], v[1]);
-            }
+            for (int n = 0; n < NN; n += 2)   // absent neighbours carry multiplicity 0; dead lanes never store
+                w2[i][n / 2] = kernel_weight_pair(pack_f32x2(s_g[n * 3], s_g[n * 3 + 3]), pack_f32x2(s_g[n * 3 + 1], s_g[n * 3 + 4]),
+                                                  pack_f32x2(s_g[n * 3 + 2], s_g[n * 3 + 5]), rk, nis2, pack_f32x2(s_mult[n], s_mult[n + 1]));
         }
     }
 
@@ -174,22 +169,19 @@ __device__ __forceinline__ void direct_weights(uint64_t (&w2)[KG][NN / 2], const
 #pragma unroll
     for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
     const float inv_sigma = 1.0f / g.sigma;
+    const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
+    (void)a_ok; (void)nn;  // absent neighbours carry multiplicity 0 in the list; dead lanes never store
 #pragma unroll
     for (int i = 0; i < KG; ++i) {
         const float kx = __ldg(g.kernels + (k0 + i) * 3), ky = __ldg(g.kernels + (k0 + i) * 3 + 1),
                     kz = __ldg(g.kernels + (k0 + i) * 3 + 2);
-        const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
-                    rz = R[6] * kx + R[7] * ky + R[8] * kz;
+        const KPoint2 rk = kpoint2(R[0] * kx + R[1] * ky + R[2] * kz, R[3] * kx + R[4] * ky + R[5] * kz,
+                                   R[6] * kx + R[7] * ky + R[8] * kz);
 #pragma unroll
         for (int n = 0; n < NN; n += 2) {
-            float v[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int m = n_first + n + e;
-                const float t = kernel_weight_fast(s_g[m * 3], s_g[m * 3 + 1], s_g[m * 3 + 2], rx, ry, rz, inv_sigma);
-                v[e] = (a_ok && m < nn) ? t * s_mult[m] : 0.f;
-            }
-            w2[i][n / 2] = pack_f32x2(v[0], v[1]);
+            const int m = n_first + n;
+            w2[i][n / 2] = kernel_weight_pair(pack_f32x2(s_g[m * 3], s_g[m * 3 + 3]), pack_f32x2(s_g[m * 3 + 1], s_g[m * 3 + 4]),
+                                              pack_f32x2(s_g[m * 3 + 2], s_g[m * 3 + 5]), rk, nis2, pack_f32x2(s_mult[m], s_mult[m + 1]));
         }
     }
 }

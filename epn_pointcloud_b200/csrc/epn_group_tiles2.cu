@@ -164,20 +164,24 @@ inter_scatter_kernel(const float *__restrict__ dG, long long stride_b, long long
         float R[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) R[i] = __ldg(g.anchors + aa * 9 + i);
+        const float inv_sigma = 1.0f / g.sigma;
+        const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
+        uint64_t gx[SC_NB / 2], gy[SC_NB / 2], gz[SC_NB / 2], mm[SC_NB / 2];
+#pragma unroll
+        for (int j = 0; j < SC_NB; j += 2) {   // absent neighbours carry multiplicity 0; dead lanes never accumulate
+            const int n = n0 + j;
+            gx[j / 2] = pack_f32x2(s_g[n * 3], s_g[n * 3 + 3]);
+            gy[j / 2] = pack_f32x2(s_g[n * 3 + 1], s_g[n * 3 + 4]);
+            gz[j / 2] = pack_f32x2(s_g[n * 3 + 2], s_g[n * 3 + 5]);
+            mm[j / 2] = pack_f32x2(s_mult[n], s_mult[n + 1]);
+        }
 #pragma unroll
         for (int k = 0; k < SC_KS; ++k) {
             const float kx = __ldg(g.kernels + k * 3), ky = __ldg(g.kernels + k * 3 + 1), kz = __ldg(g.kernels + k * 3 + 2);
-            const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
-                        rz = R[6] * kx + R[7] * ky + R[8] * kz;
-            float wv[SC_NB];
+            const KPoint2 rk = kpoint2(R[0] * kx + R[1] * ky + R[2] * kz, R[3] * kx + R[4] * ky + R[5] * kz,
+                                       R[6] * kx + R[7] * ky + R[8] * kz);
 #pragma unroll
-            for (int j = 0; j < SC_NB; ++j) {
-                const int n = n0 + j;
-                const float v = kernel_weight_fast(s_g[n * 3], s_g[n * 3 + 1], s_g[n * 3 + 2], rx, ry, rz, 1.0f / g.sigma);
-                wv[j] = (a_ok && n < nn) ? v * s_mult[n] : 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < SC_NB; j += 2) w2[k][j / 2] = pack_f32x2(wv[j], wv[j + 1]);
+            for (int j = 0; j < SC_NB / 2; ++j) w2[k][j] = kernel_weight_pair(gx[j], gy[j], gz[j], rk, nis2, mm[j]);
         }
     }
     // destination rows of this thread's 4 neighbours (element offset of [q, a] inside one channel plane)

@@ -288,22 +288,20 @@ inter_fused_kernel(FusedParams P) {
 #pragma unroll
                 for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + aa * 9 + i);
                 const float inv_sigma = 1.0f / P.g.sigma;
+                const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
 #pragma unroll
                 for (int i = 0; i < KG; ++i) {
                     const float kx = __ldg(P.g.kernels + (k0 + i) * 3), ky = __ldg(P.g.kernels + (k0 + i) * 3 + 1),
                                 kz = __ldg(P.g.kernels + (k0 + i) * 3 + 2);
-                    const float rx = R[0] * kx + R[1] * ky + R[2] * kz, ry = R[3] * kx + R[4] * ky + R[5] * kz,
-                                rz = R[6] * kx + R[7] * ky + R[8] * kz;
+                    const KPoint2 rk = kpoint2(R[0] * kx + R[1] * ky + R[2] * kz, R[3] * kx + R[4] * ky + R[5] * kz,
+                                               R[6] * kx + R[7] * ky + R[8] * kz);
 #pragma unroll
                     for (int n = 0; n < NN; n += 2) {
-                        float v[2];
-#pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int m = MODE == 1 ? n + e : n_first + n + e;
-                            const float t = kernel_weight_fast(L.g[m * 3], L.g[m * 3 + 1], L.g[m * 3 + 2], rx, ry, rz, inv_sigma);
-                            v[e] = (a_ok && n + e < nn) ? t * L.mult[m] : 0.f;
-                        }
-                        w2[i][n / 2] = pack_f32x2(v[0], v[1]);
+                        // absent neighbours (n >= nn) have multiplicity 0 in the list: their weights come out as 0
+                        const int m = (MODE == 1 ? 0 : n_first) + n;
+                        w2[i][n / 2] = kernel_weight_pair(pack_f32x2(L.g[m * 3], L.g[m * 3 + 3]), pack_f32x2(L.g[m * 3 + 1], L.g[m * 3 + 4]),
+                                                          pack_f32x2(L.g[m * 3 + 2], L.g[m * 3 + 5]), rk, nis2,
+                                                          pack_f32x2(L.mult[m], L.mult[m + 1]));
                     }
                 }
             }

@@ -49,6 +49,43 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
     return d;
 }
 
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Rotated kernel point r = R_a kappa_k broadcast into both halves of three fp32x2 registers (hoisted per (anchor, k)).
+struct KPoint2 {
+    uint64_t x, y, z;
+};
+__device__ __forceinline__ KPoint2 kpoint2(float rx, float ry, float rz) {
+    return KPoint2{pack_f32x2(rx, rx), pack_f32x2(ry, ry), pack_f32x2(rz, rz)};
+}
+// Kernel weights of TWO neighbours against one rotated kernel point, multiplicities folded in, as one fp32x2 pair:
+//   ( m0 * relu(1 - |g0 - r|^2 / sigma),  m1 * relu(1 - |g1 - r|^2 / sigma) )
+// The arithmetic of kernel_weight_fast per half, issued as packed fp32x2 instructions (8 packed + 2 max instead of
+// ~24 scalar ones; ptxas contracts the packed squares and adds into FFMA2, so |g - r|^2 carries two roundings fewer
+// than the scalar form: the weights move by <= 2e-7 absolute, far inside the 1e-4 bar -- the op-surface function
+// epn_inter_weights_f32 keeps the reference's exact operation order, kernel_weight above).  The
+// multiplicity (>= 0, 0 for absent neighbours) is multiplied in before the max, which gives the same value.
+// g*: the two neighbours' offsets (lo half = neighbour 0); neg_inv_sigma2 = (-1/sigma, -1/sigma); m2 = (m0, m1).
+__device__ __forceinline__ uint64_t kernel_weight_pair(uint64_t gx, uint64_t gy, uint64_t gz, const KPoint2 &r,
+                                                       uint64_t neg_inv_sigma2, uint64_t m2) {
+    const uint64_t minus1 = pack_f32x2(-1.0f, -1.0f), one = pack_f32x2(1.0f, 1.0f);
+    const uint64_t dx = fma_f32x2(r.x, minus1, gx), dy = fma_f32x2(r.y, minus1, gy), dz = fma_f32x2(r.z, minus1, gz);  // g - r, exact
+    const uint64_t d = add_f32x2(add_f32x2(mul_f32x2(dx, dx), mul_f32x2(dy, dy)), mul_f32x2(dz, dz));
+    const uint64_t t = mul_f32x2(fma_f32x2(d, neg_inv_sigma2, one), m2);
+    float t0, t1;
+    unpack_f32x2(t, t0, t1);
+    return pack_f32x2(fmaxf(t0, 0.0f), fmaxf(t1, 0.0f));
+}
+
 // Matrix operand of the generic GEMM: element (row, col) of slice z lives at
 // ptr + z*stride_z + row*stride_row + col*stride_col.  For A rows are m and
 // cols are k; for B rows are k and cols are n.
