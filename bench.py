@@ -167,11 +167,14 @@ class Workload:
         gemm_f = group_f = scatter_f = 0.0
         group_b = scatter_b = intra_b = 0.0
         fused_b = fused_f = 0.0
+        ifu_b = ifu_f = 0.0
         for c_in, c_out, p_in, p, k in self.layer_table():
             inter_gemm = 2.0 * c_out * c_in * KS * p * A
             intra_gemm = 2.0 * c_out * c_out * KN * p * A
             has_dx = c_in > 1  # layer 0: feats == 1, no dfeats
-            gemm_f += inter_gemm * (2 + (1 if has_dx else 0)) + intra_gemm * 3          # fwd + dW (+ dX)
+            # channel-GEMM kernels: dW (+ dX) of the inter conv, its forward only for layer 0 (the other layers'
+            # forward GEMM runs inside the fused inter kernel and is counted there), fwd + dX + dW of the intra conv
+            gemm_f += inter_gemm * 2 + intra_gemm * 3
             spatial = 2.0 * c_in * p * A * KS * k + 11.0 * p * A * KS * k
             group_f += spatial                                                          # forward only: dW reads the kept tiles
             scatter_f += spatial if has_dx else 0.0
@@ -182,9 +185,12 @@ class Workload:
             intra_b += 4.0 * c_out * p * A + 4.0 * c_out * KN * p * A                   # training forward gather into kept tiles
             fused_b += feats_in + 12.0 * p_in + 4.0 * c_out * p * A + 4.0 * p * k + 8.0 * c_out * p * A
             fused_f += spatial + inter_gemm + intra_gemm
+            if has_dx:   # the layers the fused inter-conv kernel runs (layer 0 has its own single-channel kernel)
+                ifu_b += feats_in + 12.0 * p_in + 4.0 * c_out * p * A + 4.0 * p * k      # fused InterSO3Conv bytes
+                ifu_f += spatial + inter_gemm
         return {"channel_gemm": (gemm_f * clouds, None), "inter_group_fwd": (group_f * clouds, group_b * clouds),
                 "inter_group_bwd_scatter": (scatter_f * clouds, scatter_b * clouds), "intra_group": (None, intra_b * clouds),
-                "fused_forward": (fused_f * clouds, fused_b * clouds)}
+                "fused_forward": (fused_f * clouds, fused_b * clouds), "inter_fused_fwd": (ifu_f * clouds, ifu_b * clouds)}
 
 
 class ClockSampler:
@@ -511,10 +517,15 @@ def main():
         if t <= 0:
             return None
         per_launch = max(kernel_n[cls], 1)
-        if cls == "channel_gemm":
+        if cls in ("channel_gemm", "inter_fused_fwd"):
             ach = flops / t / 1e12
             r = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                  "note": "algorithmic fp32 flops vs the measured sustained bf16 cuBLAS rate; the bf16x3 scheme caps frac at 1/3"}
+            if cls == "inter_fused_fwd":   # both accountings of SURVEY 8(d); the tensor one binds (larger ideal time)
+                r["hbm_frac"] = nbytes / t / 1e9 / hbm_peak
+                r["algorithmic_bytes"] = nbytes
+                r["note"] = ("fused InterSO3Conv (gather + spatial contraction + channel GEMM): algorithmic fp32 flops vs the "
+                             "sustained bf16 rate (x3 MMAs per product: cap 1/3); HBM accounting in hbm_frac (not binding)")
             alg = flops
         else:
             ach = nbytes / t / 1e9
@@ -533,7 +544,7 @@ def main():
                   "per_launch": {"algorithmic": alg / per_launch, "avg_ms": kernel_ms[cls] / per_launch}})
         return r
 
-    rooflines = {c: roof_of(c) for c in ("channel_gemm", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group")}
+    rooflines = {c: roof_of(c) for c in ("channel_gemm", "inter_fused_fwd", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group")}
     rooflines = {c: r for c, r in rooflines.items() if r is not None}
     dom = max(rooflines, key=lambda c: rooflines[c]["ms_per_step"])
 
