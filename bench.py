@@ -160,7 +160,7 @@ class Workload:
                 p_in = p
         return rows
 
-    def algorithmic_work(self, clouds):
+    def algorithmic_work(self, clouds, fused=True):
         """Per-step algorithmic flops / bytes per kernel class (formulas of SURVEY.md 8(d), fp32) + the fused-layer
         totals of the forward."""
         A = N_ANCHORS
@@ -176,11 +176,12 @@ class Workload:
             # forward GEMM runs inside the fused inter kernel and is counted there), fwd + dX + dW of the intra conv
             gemm_f += inter_gemm * 2 + intra_gemm * 3
             spatial = 2.0 * c_in * p * A * KS * k + 11.0 * p * A * KS * k
-            group_f += spatial                                                          # forward only: dW reads the kept tiles
             scatter_f += spatial if has_dx else 0.0
             grouped = 4.0 * c_in * KS * p * A
             feats_in = 4.0 * c_in * p_in * A if has_dx else 0.0
-            group_b += feats_in + 12.0 * p_in + 4.0 * p * k + grouped
+            if not (fused and has_dx):   # grouping-only kernels: every layer without the fused kernel, else layer 0 only
+                group_f += spatial                                                      # forward only: dW reads the kept tiles
+                group_b += feats_in + 12.0 * p_in + 4.0 * p * k + grouped
             scatter_b += (feats_in + 12.0 * p_in + 4.0 * p * k + grouped) if has_dx else 0.0
             intra_b += 4.0 * c_out * p * A + 4.0 * c_out * KN * p * A                   # training forward gather into kept tiles
             fused_b += feats_in + 12.0 * p_in + 4.0 * c_out * p * A + 4.0 * p * k + 8.0 * c_out * p * A
@@ -504,7 +505,7 @@ def main():
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback"
     clouds_per_gpu = items * wl.units_per_item
-    work = wl.algorithmic_work(clouds_per_gpu)
+    work = wl.algorithmic_work(clouds_per_gpu, fused=kernel_ms.get("inter_fused_fwd", 0.0) > 0.0)
     traffic_tab = {}
     try:  # measured DRAM bytes per class from the committed ncu pass of the same step
         traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_step.json")))
