@@ -413,8 +413,10 @@ class Runner:
             res["loss"] = loss_host
         return res
 
-    def measure_forward(self, model, x_dev, steps, warmup):
-        model.eval()
+    def measure_forward(self, model, x_dev, steps, warmup, eval_mode=False):
+        """no_grad forward.  eval_mode False: module in training mode (BatchNorm batch statistics) -- the mode the
+        reference's forward is timed in (reference_gpu_block); True: evaluation mode (running statistics)."""
+        model.train(not eval_mode)
 
         def fwd():
             with torch.no_grad():
@@ -565,9 +567,12 @@ def main():
     if extras:
         # ---- inference forward of the same network, same batch (the >= 10x reference-GPU-forward target)
         fwd_ms = R.measure_forward(S["model"], S["x_dev"], max(args.steps // 2, 3), 2)
+        fwd_eval_ms = R.measure_forward(S["model"], S["x_dev"], max(args.steps // 2, 3), 2, eval_mode=True)
         fwd_kernel_ms, _ = class_times(lambda: R.measure_forward(S["model"], S["x_dev"], 1, 0))
         ff, fb = work["fused_forward"]
         line["forward"] = {"value": world * clouds_per_gpu / (fwd_ms * 1e-3), "unit": "clouds/s", "ms": fwd_ms,
+                           "mode": "no_grad, module in training mode (BatchNorm batch statistics) -- as the reference forward is timed",
+                           "eval_mode_ms": fwd_eval_ms, "eval_mode_clouds_per_s": world * clouds_per_gpu / (fwd_eval_ms * 1e-3),
                            "kernel_ms": {k: v for k, v in fwd_kernel_ms.items() if v > 0},
                            "vs_fused_layer_roofline": {
                                "algorithmic_GB": fb / 1e9, "algorithmic_TFLOP": ff / 1e12,

@@ -69,6 +69,12 @@ def norm_act(norm, x, act, residual=None, bias=None):
                     norm.running_mean.add_((mean - norm.running_mean) * m)
                     norm.running_var.add_((var - norm.running_var) * m)
         return y
+    if (fusable and isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats
+            and norm.running_mean is not None and not (torch.is_grad_enabled() and x.requires_grad)):
+        # evaluation mode: per-channel affine map from the running statistics, one pass (no statistics kernels)
+        mean = norm.running_mean if bias is None else norm.running_mean - bias.detach()
+        stats = torch.stack((mean, torch.rsqrt(norm.running_var + norm.eps))).contiguous()
+        return ops.norm_act_fwd(x, norm.weight, norm.bias, 2, norm.eps, 0.01, residual, stats=stats)[0]
     if bias is not None:
         x = x + bias.view(1, -1, 1, 1)
     out = norm(x)

@@ -45,6 +45,10 @@ constexpr int FU_CTRL = 32;   // control warp
 template <int MODE> struct FuCfg;
 template <> struct FuCfg<1> { static constexpr int NN = 16, KG = 6, PTS = 2, GCH = 4, CAP = 16; };
 template <> struct FuCfg<2> { static constexpr int NN = 32, KG = 3, PTS = 1, GCH = 8, CAP = DEDUP_MAX_RAW; };
+// MODE 3 ("halves"): ONE point per CTA whose distinct neighbours are dealt to two pseudo-points (rows 0..63 and
+// 64..127 of the MMA); the producers are MODE 1's (6 kernel points per thread: one shared-memory load feeds twice
+// the FMAs of MODE 2), the channel GEMM is linear in G so the two partial results are simply summed in the epilogue.
+template <> struct FuCfg<3> { static constexpr int NN = 16, KG = 6, PTS = 2, GCH = 4, CAP = DEDUP_MAX_RAW; };
 
 struct FusedParams {
     const float *feats;      // [b, c, p_in, 60]
@@ -78,6 +82,9 @@ __global__ void __launch_bounds__(FuCfg<MODE>::PTS *FU_LANES *(FU_KS / FuCfg<MOD
 inter_fused_kernel(FusedParams P) {
     using C = FuCfg<MODE>;
     constexpr int NN = C::NN, KG = C::KG, PTS = C::PTS, GCH = C::GCH, NA = FU_NA, CCH = FU_CCH;
+    constexpr bool HALVES = MODE == 3;            // the PTS row blocks are neighbour subsets of ONE point
+    constexpr int NLIST = HALVES ? 1 : PTS;       // neighbour lists (= real points) of the CTA
+    constexpr int PASS_NN = HALVES ? 2 * NN : NN; // distinct neighbours one pass covers
     constexpr int GROUPS = FU_KS / KG;
     constexpr int PT_THR = FU_LANES * GROUPS;     // producer threads per point
     constexpr int NPROD = PTS * PT_THR;           // producer threads (480 in both modes)
@@ -99,7 +106,7 @@ inter_fused_kernel(FusedParams P) {
     uint8_t *a_tiles = smem;                                               // [2][KBG] k-blocks
     float *Fs = reinterpret_cast<float *>(smem + A_BYTES);                 // [PTS][2][CCH][NN][NA]
     uint8_t *ring = reinterpret_cast<uint8_t *>(Fs + PTS * 2 * CCH * NN * NA);  // weight ring, nst stages
-    __shared__ NeighbourList<C::CAP> s_L[PTS];
+    __shared__ NeighbourList<C::CAP> s_L[NLIST];
     __shared__ __align__(8) uint64_t s_gbar[PTS][2];   // gather buffers: bytes landed
     __shared__ __align__(8) uint64_t s_wfull[8], s_wempty[8];
     __shared__ __align__(8) uint64_t s_afull[2], s_afree[2], s_accum;
@@ -136,111 +143,106 @@ inter_fused_kernel(FusedParams P) {
     //      part in the three barriers of dedup_row
     {
         constexpr int DW = MODE == 1 ? 1 : 4;                      // warps per point (rows of <= 16 / <= 128 slots)
-        const bool worker = tid < PTS * DW * 32;
+        const bool worker = tid < NLIST * DW * 32;
         const int dpt = worker ? tid / (DW * 32) : 0;
-        const int dpi = P.p_off + blockIdx.x * PTS + dpt;
+        const int dpi = P.p_off + blockIdx.x * NLIST + dpt;
         dedup_row(s_L[dpt], P.idx + ((size_t)z * P.p + dpi) * P.nn, worker ? P.nn : 0, P.g.xyz + (size_t)z * 3 * P.p_in,
                   P.g.centers + (size_t)z * 3 * P.p, P.p_in, P.p, dpi, worker ? tid - dpt * DW * 32 : (1 << 20),
                   worker ? DW * 32 : 1, [] { __syncthreads(); });
     }
     const int pt = is_ctrl ? 0 : tid / PT_THR;
     const int ptid = tid - pt * PT_THR;
-    const int pl = blockIdx.x * PTS + pt;
+    const int pl = HALVES ? blockIdx.x : blockIdx.x * PTS + pt;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = s_tmem;
     // passes over the distinct neighbours (MODE 1: always one; MODE 2: ceil(distinct / 32), CTA-uniform as PTS == 1)
-    const int npass = MODE == 1 ? 1 : max(1, (s_L[0].total + NN - 1) / NN);
+    const int npass = MODE == 1 ? 1 : max(1, (s_L[0].total + PASS_NN - 1) / PASS_NN);
     const int total_gran = npass * ngran;
 
-    if (is_ctrl) {
-        // ------------------------------------------------------------ control warp: W ring + MMA issue (one thread)
-        if (tid == NPROD) {
-            // One thread feeds the tensor pipe, so this loop is written for instruction count: no divisions, slot /
-            // parity counters advanced incrementally, descriptors = constant base + small offset (a 16-k step of a
-            // C_out = 64 layer is only 96 tensor-core cycles; the first version of this loop spent ~1800 cycles of
-            // dependent scalar code per step and starved the producers of A buffers).
-            const uint32_t sps = (uint32_t)P.sps;                      // 16-k steps per ring stage (divides STEPS_G)
-            const int stages_g = STEPS_G / (int)sps;                   // ring stages per granule
-            const int total_stages = total_gran * stages_g, stages_pass = ngran * stages_g;
-            const uint32_t ring_u32 = smem_u32(ring);
-            const uint32_t half_bytes = (uint32_t)P.trb * 32u;
-            const uint32_t nst = (uint32_t)P.nst;
-            const uint32_t wfull0 = smem_u32(&s_wfull[0]), wempty0 = smem_u32(&s_wempty[0]);
-            // weight tiles in "step" layout (launch_inter_w_tiles_kperm, steps = 1): 16-k step jw is ONE contiguous
-            // block [hi: 2 k-chunks x trb rows][lo: ...] of step_bytes, so a stage of `sps` steps is one bulk copy
-            const uint8_t *wsrc = P.Wt;
-            int jw_load = 0;             // stage (within the pass) the next load fetches
-            uint32_t lslot = 0;          // ring slot the next load fills
-            auto load_w = [&]() {
-                const uint32_t bar = wfull0 + 8u * lslot;
-                mbar_arrive_expect_tx(bar, stage_bytes);
-                bulk_g2s(ring_u32 + lslot * stage_bytes, wsrc, stage_bytes, bar);
-                wsrc += stage_bytes;
-                if (++jw_load == stages_pass) { jw_load = 0; wsrc = P.Wt; }   // every pass re-streams W
-                if (++lslot == nst) lslot = 0;
-            };
-            int loaded = 0;
-            for (; loaded < (int)nst && loaded < total_stages; ++loaded) load_w();
-            const uint32_t idesc = instr_desc_bf16_m128(P.trb);
-            const uint32_t b_lbo = (uint32_t)P.trb * 16u;
-            const uint64_t a_desc0 = smem_desc(smem_u32(a_tiles), A_LBO, 128);      // + (byte offset >> 4)
-            const uint64_t b_desc0 = smem_desc(ring_u32, b_lbo, 128);
-            const uint32_t stage16 = stage_bytes >> 4, step16 = step_bytes >> 4, half16 = half_bytes >> 4;
-            uint32_t slot = 0, wpar = 0;     // slot / parity of the stage being consumed
-            uint32_t eslot = 0, epar = 0;    // slot / parity of the stage whose MMAs are awaited before its slot is refilled
-            uint32_t accumulate = 0, sub = 0;
-            bool first = true;
-            const uint32_t afull0 = smem_u32(&s_afull[0]), afree0 = smem_u32(&s_afree[0]);
-            for (int gi = 0; gi < total_gran; ++gi) {
-                const uint32_t ab = (uint32_t)gi & 1u;
-                mbar_wait_q(afull0 + 8u * ab, ((uint32_t)gi >> 1) & 1u);
-                tc_fence_after();
-                const uint64_t a_g = a_desc0 + (uint64_t)(ab * (A_BUF >> 4));
+    // warp index as a value the compiler can prove warp-uniform (shuffle from lane 0): the control warp's loop below
+    // then stays converged and its descriptors / barrier addresses live in uniform registers
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+    if (warp_u == NPWARPS) {
+        // ------------------------------------------------------------ control warp: W ring + MMA issue
+        // The WHOLE warp runs this loop converged; one elected lane issues each MMA / commit / bulk copy
+        // (epn_umma.cuh, "warp-converged issue").  The weight ring is refilled from the same loop: a slot is reloaded
+        // as soon as a non-blocking test shows that the MMAs that read it have completed (blocking only when the
+        // stage about to be consumed has not been requested yet), so up to nst - 1 loads stay in flight.
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t sps = (uint32_t)P.sps;                      // 16-k steps per ring stage (divides STEPS_G)
+        const int stages_g = STEPS_G / (int)sps;                   // ring stages per granule
+        const int total_stages = total_gran * stages_g, stages_pass = ngran * stages_g;
+        const uint32_t ring_u32 = smem_u32(ring);
+        const uint32_t nst = (uint32_t)P.nst;
+        const uint32_t wfull0 = smem_u32(&s_wfull[0]), wempty0 = smem_u32(&s_wempty[0]);
+        // weight tiles in "step" layout (launch_inter_w_tiles_kperm, steps = 1): 16-k step jw is ONE contiguous
+        // block [hi: 2 k-chunks x trb rows][lo: ...] of step_bytes, so a stage of `sps` steps is one bulk copy
+        const uint8_t *wsrc = P.Wt;
+        int jw = 0;                      // stage within the pass (every pass re-streams W)
+        int loaded = 0;                  // stages requested so far
+        uint32_t lslot = 0, lpar = 1;    // first round: the slots are empty (the test of the preceding phase passes)
+        auto load_w = [&]() {
+            bulk_g2s_expect_elect(ring_u32 + lslot * stage_bytes, wsrc, stage_bytes, wfull0 + 8u * lslot);
+            wsrc += stage_bytes;
+            if (++jw == stages_pass) { jw = 0; wsrc = P.Wt; }
+            if (++lslot == nst) { lslot = 0; lpar ^= 1u; }
+            ++loaded;
+        };
+        const uint32_t half_bytes = (uint32_t)P.trb * 32u;
+        const uint32_t idesc = instr_desc_bf16_m128(P.trb);
+        const uint32_t b_lbo = (uint32_t)P.trb * 16u;
+        const uint64_t a_desc0 = smem_desc(smem_u32(a_tiles), A_LBO, 128);      // + (byte offset >> 4)
+        const uint64_t b_desc0 = smem_desc(ring_u32, b_lbo, 128);
+        const uint32_t stage16 = stage_bytes >> 4, step16 = step_bytes >> 4, half16 = half_bytes >> 4;
+        uint32_t slot = 0, wpar = 0;     // slot / parity of the stage being consumed
+        uint32_t accumulate = 0, sub = 0;
+        int consumed = 0;                // stages whose MMAs have been issued
+        const uint32_t afull0 = smem_u32(&s_afull[0]), afree0 = smem_u32(&s_afree[0]);
+        while (loaded < total_stages && loaded < (int)nst) load_w();
+        for (int gi = 0; gi < total_gran; ++gi) {
+            const uint32_t ab = (uint32_t)gi & 1u;
+            mbar_wait_q(afull0 + 8u * ab, ((uint32_t)gi >> 1) & 1u);
+            tc_fence_after();
+            const uint64_t a_g = a_desc0 + (uint64_t)(ab * (A_BUF >> 4));
 #pragma unroll
-                for (int s = 0; s < STEPS_G; ++s) {
-                    if (sub == 0) {
-                        mbar_wait_q(wfull0 + 8u * slot, wpar);
-                        tc_fence_after();
+            for (int s = 0; s < STEPS_G; ++s) {
+                if (sub == 0) {
+                    if (loaded == consumed) {   // ring ran dry: the stage to consume has not even been requested
+                        mbar_wait_q(wempty0 + 8u * lslot, lpar);
+                        load_w();
                     }
-                    const uint64_t a_hi = a_g + (uint64_t)((uint32_t)(s >> 1) * (A_KB >> 4) + (uint32_t)(s & 1) * (2u * A_LBO >> 4));
-                    const uint64_t a_lo = a_hi + (uint64_t)(A_PART >> 4);
-                    const uint64_t b_hi = b_desc0 + (uint64_t)(slot * stage16 + sub * step16);
-                    const uint64_t b_lo = b_hi + (uint64_t)half16;
-                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, accumulate);
-                    accumulate = 1;
-                    mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, 1);
-                    mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, 1);
-                    if (++sub == sps) {
-                        sub = 0;
-                        mma_commit(wempty0 + 8u * slot);
-                        if (++slot == nst) { slot = 0; wpar ^= 1u; }
-                        // refill the slot of the PREVIOUS stage (its MMAs finish before this stage's do, so this wait
-                        // does not drain the tensor pipe)
-                        if (!first) {
-                            if (loaded < total_stages) {
-                                mbar_wait_q(wempty0 + 8u * eslot, epar);
-                                load_w();
-                                ++loaded;
-                            }
-                            if (++eslot == nst) { eslot = 0; epar ^= 1u; }
-                        }
-                        first = false;
-                    }
+                    mbar_wait_q(wfull0 + 8u * slot, wpar);
+                    tc_fence_after();
                 }
-                mma_commit(afree0 + 8u * ab);  // A tiles of this granule consumed
+                const uint64_t a_hi = a_g + (uint64_t)((uint32_t)(s >> 1) * (A_KB >> 4) + (uint32_t)(s & 1) * (2u * A_LBO >> 4));
+                const uint64_t a_lo = a_hi + (uint64_t)(A_PART >> 4);
+                const uint64_t b_hi = b_desc0 + (uint64_t)(slot * stage16 + sub * step16);
+                const uint64_t b_lo = b_hi + (uint64_t)half16;
+                mma_bf16_ss_elect(tmem_u, a_hi, b_hi, idesc, accumulate);
+                accumulate = 1;
+                mma_bf16_ss_elect(tmem_u, a_hi, b_lo, idesc, 1);
+                mma_bf16_ss_elect(tmem_u, a_lo, b_hi, idesc, 1);
+                if (++sub == sps) {
+                    sub = 0;
+                    mma_commit_elect(wempty0 + 8u * slot);   // the slot may be refilled once these MMAs have read it
+                    if (++slot == nst) { slot = 0; wpar ^= 1u; }
+                    ++consumed;
+                    // refill every slot whose MMAs have completed (never more than nst requests ahead of consumption)
+                    while (loaded < total_stages && loaded - consumed < (int)nst && mbar_test_wait(wempty0 + 8u * lslot, lpar)) load_w();
+                }
             }
-            mma_commit(smem_u32(&s_accum));
+            mma_commit_elect(afree0 + 8u * ab);  // A tiles of this granule consumed
         }
-        __syncwarp();  // the other 31 lanes sleep here instead of polling the accumulator barrier for the whole kernel
+        mma_commit_elect(smem_u32(&s_accum));
     } else {
         // ------------------------------------------------------------ producers
         const int aa = ptid % FU_LANES, grp = ptid / FU_LANES;
         const int k0 = grp * KG;
         constexpr bool a_ok = true;
         const float *F = P.feats + (size_t)z * P.c * P.p_in * NA;
-        const NeighbourList<C::CAP> &L = s_L[pt];
+        const NeighbourList<C::CAP> &L = s_L[HALVES ? 0 : pt];
         float *Fp = Fs + (size_t)pt * 2 * CCH * NN * NA;
         const int total_nn = L.total;
         constexpr int bar_id = 1;   // named barrier of the producer threads (points advance in lockstep)
@@ -276,9 +278,20 @@ inter_fused_kernel(FusedParams P) {
         int gi = 0;  // granules produced so far by this CTA
         const int nchunks = P.c / CCH;
         for (int pass = 0; pass < npass; ++pass) {
-            const int n_first = pass * NN;
+            int n_first = pass * PASS_NN;
             int nn = total_nn - n_first;          // distinct neighbours of this pass
-            nn = nn < 0 ? 0 : (nn > NN ? NN : nn);
+            nn = nn < 0 ? 0 : (nn > PASS_NN ? PASS_NN : nn);
+            if (HALVES) {
+                // half 0 takes the first ceil(groups / 2) groups of four neighbours, half 1 the rest: whole groups, so
+                // that the FMA loop of half 0 (which skips groups past its count) never touches half 1's entries
+                const int n0 = (((nn + 3) >> 2) + 1) >> 1 << 2;
+                if (pt == 0) {
+                    nn = nn < n0 ? nn : n0;
+                } else {
+                    n_first += n0;
+                    nn = nn > n0 ? nn - n0 : 0;
+                }
+            }
             named_bar_sync(bar_id, NPROD);      // everybody is done with the previous pass's gather buffers
             for (int t = ptid; t < 2 * CCH * NN * NA; t += PT_THR)   // never-copied rows are zero
                 if ((t / NA) % NN >= nn) Fp[t] = 0.f;
@@ -357,7 +370,7 @@ inter_fused_kernel(FusedParams P) {
                     if (h == 0 && gi >= 2)  // the MMAs of granule gi-2 have read A[ab]
                         mbar_wait_q(afree0 + 8u * (uint32_t)ab, (uint32_t)((gi >> 1) - 1) & 1u);
                     const float *fbase = Fp + (size_t)(buf * CCH * NN) * NA + aa;
-                    if (MODE == 1) {
+                    if (MODE != 2) {
                         // 4 channels x 6 kernel points = 24 values = K' chunks 12 g + 3 grp + {0,1,2}
                         const int kcl0 = grp * 3, kc0 = g * 12 + grp * 3;
 #pragma unroll
@@ -463,7 +476,31 @@ inter_fused_kernel(FusedParams P) {
         const int q = warp & 3;                          // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                  // = pt*64 + anchor
         const int rpt = row >> 6, ra = row & 63;
-        if (rpt < PTS) {                                // warp-uniform (PTS == 1: quarters 2,3 hold dead rows)
+        if (HALVES) {
+            // rows r and r + 64 are the two partial results of (point, anchor r): quarters 2,3 hand theirs over through
+            // shared memory (the A tiles are free: every MMA has completed), quarters 0,1 add and store
+            float *stage = reinterpret_cast<float *>(a_tiles) + (size_t)(warp >> 2) * (32 * 64);   // [32 channels][64 rows]
+            float *orow = P.out + (size_t)z * P.out_sz + (size_t)blockIdx.x * NA + ra;
+            for (int cg0 = 0; cg0 * 32 < P.c_out; cg0 += NWARPS / 4) {
+                const int cg = cg0 + (warp >> 2);
+                const bool active = cg * 32 < P.c_out;   // uniform over the four warps that share a staging area
+                float v[32];
+                if (active) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), v);
+                if (active && rpt == 1) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) stage[jj * 64 + ra] = v[jj];
+                }
+                __syncthreads();
+                if (active && rpt == 0 && ra < NA) {
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) {
+                        const int o = cg * 32 + jj;
+                        if (o < P.c_out) orow[(size_t)o * P.out_so] = v[jj] + stage[jj * 64 + ra];
+                    }
+                }
+                __syncthreads();
+            }
+        } else if (rpt < PTS) {                         // warp-uniform (PTS == 1: quarters 2,3 hold dead rows)
             float *orow = P.out + (size_t)z * P.out_sz + (size_t)(blockIdx.x * PTS + rpt) * NA + ra;
             for (int cg = warp >> 2; cg * 32 < P.c_out; cg += NWARPS / 4) {
                 float v[32];
@@ -509,17 +546,27 @@ int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     const size_t smem_bytes = fixed + (size_t)nst * stage;
     static DynSmemOnce once;  // one per template instantiation
     if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE, GATHER>, (int)budget, "inter_fused_kernel")) return rc;
-    dim3 grid(p_cnt / C::PTS, bc);
+    dim3 grid(MODE == 3 ? p_cnt : p_cnt / C::PTS, bc);
     inter_fused_kernel<MODE, GATHER><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
     return check_launch("inter_fused_kernel");
 }
 
 }  // namespace
 
+// EPN_FU_HALVES=0 sends rows of more than 16 slots to MODE 2 also in inference (tuning / A-B knob)
+static bool fused_halves_enabled() {
+    static const bool on = [] { const char *e = getenv("EPN_FU_HALVES"); return e == nullptr || atoi(e) != 0; }();
+    return on;
+}
+
 // K' mode the fused kernel uses for this shape (0 = shape not covered).  keep = the caller wants the operand tiles.
 int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool keep) {
     if (ks != FU_KS || na != FU_NA || c_out > 256 || c < 4) return 0;
     if (nn <= 16 && c % 4 == 0 && p_cnt % 2 == 0) return 1;
+    // inference (no kept tiles), longer rows: the "halves" variant of the kernel, which uses MODE 1's K' order
+    // (measured: 3.10 vs 3.44 ms on the 64-channel K = 32 layer of the cls network, no gain from 128 channels on --
+    // every G value is converted twice there, which costs what the better load : FMA ratio saves)
+    if (!keep && nn <= DEDUP_MAX_RAW && c % 4 == 0 && c <= 64 && fused_halves_enabled()) return 1;
     if (nn <= (keep ? 32 : DEDUP_MAX_RAW) && c % 8 == 0) return 2;
     return 0;
 }
@@ -552,6 +599,11 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
     ProfScope prof(s, KC_INTER_FUSED);
     int gather = 1;
     if (const char *e = getenv("EPN_FU_GATHER")) gather = atoi(e);   // tuning knob (tools/fused_sweep.py)
+    if (mode == 1 && (nn > 16 || p_cnt % 2 != 0)) {   // halves variant (inference only, see inter_fused_mode)
+        if (gather == 0) return launch_fused_variant<3, 0>(P, p_cnt, bc, s);
+        if (gather == 2) return launch_fused_variant<3, 2>(P, p_cnt, bc, s);
+        return launch_fused_variant<3, 1>(P, p_cnt, bc, s);
+    }
     if (mode == 1) {
         if (gather == 0) return launch_fused_variant<1, 0>(P, p_cnt, bc, s);
         if (gather == 2) return launch_fused_variant<1, 2>(P, p_cnt, bc, s);

@@ -202,7 +202,7 @@ EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float
                                  float eps, float slope, void *stream) {
     EPN_REQUIRE_PTR(x); EPN_REQUIRE_PTR(y); EPN_REQUIRE_PTR(stats); EPN_REQUIRE_PTR(workspace);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c); EPN_REQUIRE_POS(n);
-    EPN_REQUIRE(mode == 0 || mode == 1, EPN_ERR_SHAPE, "mode must be 0 (instance) or 1 (batch)");
+    EPN_REQUIRE(mode >= 0 && mode <= 2, EPN_ERR_SHAPE, "mode must be 0 (instance), 1 (batch) or 2 (batch, given statistics)");
     EPN_REQUIRE((long long)b * c <= 2147483647LL / 2, EPN_ERR_SHAPE, "b*c too large");
     EPN_REQUIRE(workspace_bytes >= epn_norm_act_workspace_bytes(b, c), EPN_ERR_WORKSPACE, "workspace too small");
     EPN_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) == 0, EPN_ERR_ALIGN, "x, y and residual must be 16-byte aligned");
@@ -210,12 +210,17 @@ EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float
     float2 *part = static_cast<float2 *>(workspace);
     const int rows = b * c, G = mode == 0 ? rows : c;
     ProfScope prof(s, KC_NORM);
-    norm_row_stats_kernel<<<rows, NT, 0, s>>>(x, part, n);
-    int rc = check_launch("norm_row_stats_kernel");
-    if (rc) return rc;
-    norm_finalize_kernel<<<cdiv(G, 128), 128, 0, s>>>(part, stats, b, c, n, mode, eps);
-    rc = check_launch("norm_finalize_kernel");
-    if (rc) return rc;
+    int rc = 0;
+    if (mode == 2) {
+        mode = 1;   // evaluation-mode BatchNorm: the caller's per-channel (mean, rstd) are applied as they are
+    } else {
+        norm_row_stats_kernel<<<rows, NT, 0, s>>>(x, part, n);
+        rc = check_launch("norm_row_stats_kernel");
+        if (rc) return rc;
+        norm_finalize_kernel<<<cdiv(G, 128), 128, 0, s>>>(part, stats, b, c, n, mode, eps);
+        rc = check_launch("norm_finalize_kernel");
+        if (rc) return rc;
+    }
     dim3 grid(cdiv(n, NT * 4 * 4) > 0 ? cdiv(n, NT * 4 * 4) : 1, rows);
     if (rows > 65535) {
         set_error("epn_norm_act_fwd_f32: b*c = %d rows exceed the grid limit", rows);

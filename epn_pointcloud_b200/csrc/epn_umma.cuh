@@ -137,6 +137,47 @@ __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+// ---------------------------------------------------------------- warp-converged issue (elect.sync)
+// The variants below are executed by a WHOLE converged warp; one elected lane issues the instruction.  Keeping the
+// issuing warp converged lets the compiler hold descriptors / addresses in uniform registers: under a divergent
+// `if (lane == 0)` it wraps every tcgen05 / bulk-copy instruction (whose operands are uniform registers) in an
+// ELECT + R2UR + BRA.U.ANY loop over the active lanes, ~25 dependent instructions per MMA (measured ~1100 cycles per
+// 16-k step of three MMAs in the fused inter conv, which made the issuing thread the kernel's bottleneck).
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar) : "memory");
+}
+// arrive.expect_tx + one bulk copy global -> shared, by one elected lane
+__device__ __forceinline__ void bulk_g2s_expect_elect(uint32_t dst_smem, const void *src_gmem, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%3], %2;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
+        ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
+// non-blocking phase test
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0;
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];

@@ -433,15 +433,20 @@ def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True,
     return dfeats, dW
 
 
-def norm_act_fwd(x, gamma, beta, mode, eps, slope, residual=None):
+def norm_act_fwd(x, gamma, beta, mode, eps, slope, residual=None, stats=None):
     """x [b,c,p,a] -> (y, stats[2,G]); mode 0 = InstanceNorm2d(affine=False), 1 = BatchNorm2d (batch statistics),
+    2 = BatchNorm2d in evaluation mode (`stats` [2,c] = per-channel (mean, 1/sqrt(var+eps)) given by the caller),
     followed by leaky_relu(slope)  (SPConvNets/utils/base_so3conv.py:43,55-57,107,119-125); `residual` (same shape)
     is added to the result in the same pass (the skip connection, base_so3conv.py:209-211)."""
-    _require_cuda(x, gamma, beta, residual)
+    _require_cuda(x, gamma, beta, residual, stats)
     b, c = x.shape[0], x.shape[1]
     n = x[0, 0].numel()
     y = torch.empty_like(x)
-    stats = torch.empty(2, b * c if mode == 0 else c, dtype=torch.float32, device=x.device)
+    if mode == 2:
+        if stats is None or tuple(stats.shape) != (2, c) or stats.dtype != torch.float32 or not stats.is_contiguous():
+            raise ValueError("mode 2 needs stats [2, c] float32 contiguous")
+    else:
+        stats = torch.empty(2, b * c if mode == 0 else c, dtype=torch.float32, device=x.device)
     L = _lib.lib()
     with torch.cuda.device(x.device):
         wsb = L.epn_norm_act_workspace_bytes(b, c)

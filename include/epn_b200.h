@@ -209,6 +209,8 @@ int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, fl
  * y = leaky_relu(norm(x) * gamma + beta, slope) on x [b, c, n] (n = points*anchors):
  *   mode 0: InstanceNorm2d(affine=False) -> leaky_relu  (SPConvNets/utils/base_so3conv.py:43,55-57)
  *   mode 1: BatchNorm2d, batch statistics, affine -> leaky_relu  (base_so3conv.py:107,119-125,193,209)
+ *   mode 2 (forward only): BatchNorm2d in evaluation mode -- stats [2*c] is an INPUT holding the per-channel
+ *           (mean, 1/sqrt(running_var + eps)); one apply pass, no statistics kernels
  * gamma/beta [c] may be NULL (= 1 / 0).  stats [2*G] receives (mean, rstd) per group, G = b*c (mode 0)
  * or c (mode 1); the backward needs it, and the caller derives BatchNorm's running statistics from it.
  * residual [b, c, n] (NULL = none): the skip connection of SeparableSO3ConvBlock fused into the same pass,

@@ -737,6 +737,35 @@ def test_fused_norm_act_with_skip_bias_and_residual(E, kind):
         assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-4
 
 
+def test_fused_norm_act_batchnorm_eval_mode(E):
+    """Evaluation-mode BatchNorm2d -> leaky_relu (+ skip bias, + residual) as ONE apply pass with the running
+    statistics (no statistics kernels), against torch in float64; the running statistics stay untouched."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from epn_pointcloud_b200 import _lib
+    from epn_pointcloud_b200.blocks import norm_act
+    b, c, p, a = 3, 8, 16, 60
+    gen = torch.Generator().manual_seed(78)
+    x0 = torch.randn(b, c, p, a, generator=gen) * 2.0 + 1.0
+    res0 = torch.randn(b, c, p, a, generator=gen)
+    bias0 = torch.randn(c, generator=gen)
+    mine, ref = nn.BatchNorm2d(c), nn.BatchNorm2d(c)
+    with torch.no_grad():
+        for m in (mine, ref):
+            m.running_mean.copy_(torch.linspace(-1, 1, c))
+            m.running_var.copy_(torch.linspace(0.5, 2, c))
+            m.weight.copy_(torch.linspace(0.5, 1.5, c))
+            m.bias.copy_(torch.linspace(-0.2, 0.2, c))
+    mine, ref = mine.to(DEV).eval(), ref.double().eval()
+    n0 = _lib.lib().epn_launch_count()
+    with torch.no_grad():
+        y = norm_act(mine, x0.to(DEV), F.leaky_relu, residual=res0.to(DEV), bias=bias0.to(DEV))
+        yr = F.leaky_relu(ref(x0.double() + bias0.double().view(1, -1, 1, 1))) + res0.double()
+    assert _lib.lib().epn_launch_count() - n0 == 1          # the apply kernel only
+    assert rel_err(y, yr) < 1e-6
+    assert torch.equal(mine.running_mean.cpu(), torch.linspace(-1, 1, c)) and int(mine.num_batches_tracked) == 0
+
+
 # ------------------------------------------------------------ classification head + full model (8 f2)
 def test_cls_head_vs_golden(E):
     """ClsOutBlockPointnet + PointnetSO3Conv (base_so3conv.py:358-448, so3conv/modules.py:203-235) against
