@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_c
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp != 5) {
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform
+    if (warp_u != 5) {
         // producers: every lane owns one (forward k-block, part, 8-kk group) piece of the A stage.  A warp can issue
         // these 1-KB bulk copies only at ~26 GB/s (measured: one issuing warp per SM streams 3.8 TB/s, two 6.5 TB/s,
         // while 16-KB copies reach 7.5 TB/s from a single warp), so one warp PER PIPELINE STAGE issues them: warp w
@@ -119,32 +120,32 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_c
                 bulk_g2s(st + A_STAGE + lane * b_tile, b_src + (size_t)(2 * u + lane) * b_tile, b_tile, full_bar(s));
         }
     } else {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16_m128(p.trb) | (1u << 15);  // A is MN-major
-            const uint32_t b_lbo = (uint32_t)p.trb * 16;
-            for (int i = 0; i < nu; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_STAGE;
+        // the MMA warp runs converged and issues through elect.sync (epn_umma.cuh, "warp-converged issue")
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t idesc = instr_desc_bf16_m128(p.trb) | (1u << 15);  // A is MN-major
+        const uint32_t b_lbo = (uint32_t)p.trb * 16;
+        for (int i = 0; i < nu; ++i) {
+            const int s = i % p.stages;
+            const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a0 = base + s * stage_bytes, b0 = a0 + A_STAGE;
 #pragma unroll
-                for (int ks = 0; ks < UNIT / 16; ++ks) {
-                    // 16 n per MMA = two 8-n groups 128 B apart (LBO); 8-kk groups UNIT*16 B apart (SBO)
-                    // (field order checked on the B200: the swapped assignment gives garbage)
-                    const uint64_t a_hi = smem_desc(a0 + ks * 256, 128, UNIT * 16);
-                    const uint64_t a_lo = smem_desc(a0 + A_PART + ks * 256, 128, UNIT * 16);
-                    const uint32_t bb = b0 + (ks >> 1) * b_tile + (ks & 1) * 2 * b_lbo;
-                    const uint64_t b_hi = smem_desc(bb, b_lbo, 128);
-                    const uint64_t b_lo = smem_desc(bb + (uint32_t)part_bytes(p.trb), b_lbo, 128);
-                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, (i | ks) != 0);
-                    mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, 1);
-                    mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, 1);
-                }
-                mma_commit(empty_bar(s));
+            for (int ks = 0; ks < UNIT / 16; ++ks) {
+                // 16 n per MMA = two 8-n groups 128 B apart (LBO); 8-kk groups UNIT*16 B apart (SBO)
+                // (field order checked on the B200: the swapped assignment gives garbage)
+                const uint64_t a_hi = smem_desc(a0 + ks * 256, 128, UNIT * 16);
+                const uint64_t a_lo = smem_desc(a0 + A_PART + ks * 256, 128, UNIT * 16);
+                const uint32_t bb = b0 + (ks >> 1) * b_tile + (ks & 1) * 2 * b_lbo;
+                const uint64_t b_hi = smem_desc(bb, b_lbo, 128);
+                const uint64_t b_lo = smem_desc(bb + (uint32_t)part_bytes(p.trb), b_lbo, 128);
+                mma_bf16_ss_elect(tmem_u, a_hi, b_hi, idesc, (i | ks) != 0);
+                mma_bf16_ss_elect(tmem_u, a_hi, b_lo, idesc, 1);
+                mma_bf16_ss_elect(tmem_u, a_lo, b_hi, idesc, 1);
             }
-            mma_commit(accum_bar);
+            mma_commit_elect(empty_bar(s));
         }
+        mma_commit_elect(accum_bar);
     }
     if (warp < 4) {
         mbar_wait(accum_bar, 0);

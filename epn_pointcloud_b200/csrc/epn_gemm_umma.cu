@@ -170,44 +170,43 @@ umma_gemm_kernel(UmmaGemmParams p) {
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    // the loader and the MMA warp stay CONVERGED and issue through elect.sync (epn_umma.cuh, "warp-converged issue"):
+    // their branch conditions and operands are made provably warp-uniform with shuffles from lane 0
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 
-    if (warp == 4) {
-        if (lane == 0) {
-            const uint8_t *a_src = p.A + ((size_t)blockIdx.x * p.k_blocks + kb0) * a_bytes;
-            const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.k_blocks + kb0) * b_bytes;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-                bulk_g2s(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes, full_bar(s));
-                bulk_g2s(base + s * stage_bytes + a_bytes, b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
-            }
+    if (warp_u == 4) {
+        const uint8_t *a_src = p.A + ((size_t)blockIdx.x * p.k_blocks + kb0) * a_bytes;
+        const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.k_blocks + kb0) * b_bytes;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % p.stages;
+            const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            bulk_g2s2_expect_elect(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes, base + s * stage_bytes + a_bytes,
+                                   b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16_m128(p.trb);
-            const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
-                mbar_wait(full_bar(s), ph);
-                tc_fence_after();
-                const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
+    } else if (warp_u == 5) {
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+        const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % p.stages;
+            const uint32_t ph = (uint32_t)(i / p.stages) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
 #pragma unroll
-                for (int ks = 0; ks < KB / 16; ++ks) {
-                    const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
-                    const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
-                    const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
-                    mma_bf16_ss(tmem_base, a_hi, b_hi, idesc, (i | ks) != 0);
-                    mma_bf16_ss(tmem_base, a_hi, b_lo, idesc, 1);
-                    mma_bf16_ss(tmem_base, a_lo, b_hi, idesc, 1);
-                }
-                mma_commit(empty_bar(s));  // frees the stage when these MMAs have read it
+            for (int ks = 0; ks < KB / 16; ++ks) {
+                const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
+                const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
+                const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
+                const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
+                mma_bf16_ss_elect(tmem_u, a_hi, b_hi, idesc, (i | ks) != 0);
+                mma_bf16_ss_elect(tmem_u, a_hi, b_lo, idesc, 1);
+                mma_bf16_ss_elect(tmem_u, a_lo, b_hi, idesc, 1);
             }
-            mma_commit(accum_bar);
+            mma_commit_elect(empty_bar(s));  // frees the stage when these MMAs have read it
         }
+        mma_commit_elect(accum_bar);
     } else {
         mbar_wait(accum_bar, 0);
         tc_fence_after();
@@ -354,53 +353,50 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
     uint32_t tmem_base;
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-    if (warp == 4) {
-        if (lane == 0) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int tm = tile % m_tiles, tn = tile / m_tiles;
-                const uint8_t *a_src = p.A + (size_t)tm * nkb * a_bytes;
-                const uint8_t *b_src = p.B + (size_t)tn * nkb * b_bytes;
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_arrive_expect_tx(full_bar(s), stage_bytes);
-                    bulk_g2s(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes, full_bar(s));
-                    bulk_g2s(base + s * stage_bytes + a_bytes, b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
-                }
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // provably warp-uniform: loader / MMA warps stay converged
+    if (warp_u == 4) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            const int tm = tile % m_tiles, tn = tile / m_tiles;
+            const uint8_t *a_src = p.A + (size_t)tm * nkb * a_bytes;
+            const uint8_t *b_src = p.B + (size_t)tn * nkb * b_bytes;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(empty_bar(s), ph ^ 1u);
+                bulk_g2s2_expect_elect(base + s * stage_bytes, a_src + (size_t)i * a_bytes, a_bytes,
+                                       base + s * stage_bytes + a_bytes, b_src + (size_t)i * b_bytes, b_bytes, full_bar(s));
             }
         }
-    } else if (warp == 5) {
-        if (lane == 0) {
-            const uint32_t idesc = instr_desc_bf16_m128(p.trb);
-            const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
-            int it = 0, t = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
-                const int buf = t & 1;
-                mbar_wait(acc_empty(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+    } else if (warp_u == 5) {
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+        const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
+        int it = 0, t = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
+            const int buf = t & 1;
+            mbar_wait(acc_empty(buf), ((uint32_t)(t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + (uint32_t)buf * p.tmem_cols;
+            for (int i = 0; i < nkb; ++i, ++it) {
+                const int s = it % p.stages;
+                const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+                mbar_wait(full_bar(s), ph);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)buf * p.tmem_cols;
-                for (int i = 0; i < nkb; ++i, ++it) {
-                    const int s = it % p.stages;
-                    const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-                    mbar_wait(full_bar(s), ph);
-                    tc_fence_after();
-                    const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
+                const uint32_t a0 = base + s * stage_bytes, b0 = a0 + a_bytes;
 #pragma unroll
-                    for (int ks = 0; ks < KB / 16; ++ks) {
-                        const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
-                        const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
-                        const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
-                        const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
-                        mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (i | ks) != 0);
-                        mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1);
-                        mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1);
-                    }
-                    mma_commit(empty_bar(s));
+                for (int ks = 0; ks < KB / 16; ++ks) {
+                    const uint64_t a_hi = smem_desc(a0 + ks * 2 * a_lbo, a_lbo, 128);
+                    const uint64_t a_lo = smem_desc(a0 + (uint32_t)part_bytes(TR_A) + ks * 2 * a_lbo, a_lbo, 128);
+                    const uint64_t b_hi = smem_desc(b0 + ks * 2 * b_lbo, b_lbo, 128);
+                    const uint64_t b_lo = smem_desc(b0 + (uint32_t)part_bytes(p.trb) + ks * 2 * b_lbo, b_lbo, 128);
+                    mma_bf16_ss_elect(d_tmem, a_hi, b_hi, idesc, (i | ks) != 0);
+                    mma_bf16_ss_elect(d_tmem, a_hi, b_lo, idesc, 1);
+                    mma_bf16_ss_elect(d_tmem, a_lo, b_hi, idesc, 1);
                 }
-                mma_commit(acc_full(buf));
+                mma_commit_elect(empty_bar(s));
             }
+            mma_commit_elect(acc_full(buf));
         }
     } else {
         const bool col_split = p.cols_per_z < (long long)p.n_valid;

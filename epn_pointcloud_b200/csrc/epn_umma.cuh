@@ -167,6 +167,18 @@ __device__ __forceinline__ void bulk_g2s_expect_elect(uint32_t dst_smem, const v
         "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n\t}"
         ::"r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
+// arrive.expect_tx(bytes_a + bytes_b) + two bulk copies, by one elected lane
+__device__ __forceinline__ void bulk_g2s2_expect_elect(uint32_t dst_a, const void *src_a, uint32_t bytes_a, uint32_t dst_b,
+                                                       const void *src_b, uint32_t bytes_b, uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t.reg .b32 t;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "add.u32 t, %2, %5;\n\t"
+        "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%6], t;\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%6];\n\t"
+        "@q cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%3], [%4], %5, [%6];\n\t}"
+        ::"r"(dst_a), "l"(src_a), "r"(bytes_a), "r"(dst_b), "l"(src_b), "r"(bytes_b), "r"(bar) : "memory");
+}
 // non-blocking phase test
 __device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
     uint32_t done;

@@ -608,7 +608,9 @@ def test_dw_from_kept_forward_tiles_equals_recomputed(E, kind, c_in, c_out, p, n
     if kind == "intra":  # without kept tiles the forward is the permuted GEMM: same products, different summation order
         assert rel_err(res["on"][0], res["off"][0]) < 3e-5   # the bar both hold against the fp32 SIMT engine
     else:
-        assert torch.equal(res["on"][0], res["off"][0])      # same tiles, same GEMM: bit-identical forward
+        # same tiles, same GEMM: bit-identical forward -- except where the forward without kept tiles takes the "halves"
+        # variant of the fused kernel (64 channels, rows of > 16 slots), which sums the neighbours in two partial tiles
+        assert torch.equal(res["on"][0], res["off"][0]) or rel_err(res["on"][0], res["off"][0]) < 1e-5
     assert rel_err(res["on"][1], res["off"][1]) < 5e-6       # same products, different summation order
     if res["on"][2] is not None:
         assert torch.equal(res["on"][2], res["off"][2]) or rel_err(res["on"][2], res["off"][2]) < 1e-6
