@@ -40,7 +40,39 @@ class _NormActFn(torch.autograd.Function):
         return dx, dgamma, dbeta, None, None, None, (dy if ctx.needs_input_grad[6] else None), dbias
 
 
+# ------------------------------------------------------------------ operand format of inference forwards
+# Under torch.no_grad() the convs of these wrappers run their tensor-core GEMMs on fp16 hi/lo operands (22 significand
+# bits instead of bf16 hi/lo's 16, same speed; include/epn_b200.h, epn_set_forward_operands) -- but ONLY when the
+# conv's input is known to be a normalised activation: a tensor produced by norm_act below (tagged `_epn_unit`) or the
+# constant occupancy features.  Anything of unknown provenance keeps the range-safe bf16 operands.
+_INFERENCE_OPERANDS = "f16"
+
+
+def set_inference_operands(fmt):
+    """'f16' (default) or 'bf16': operand format of no_grad forwards on normalised activations."""
+    global _INFERENCE_OPERANDS
+    if fmt not in ("f16", "bf16"):
+        raise ValueError(fmt)
+    _INFERENCE_OPERANDS = fmt
+
+
+def _mark_unit(t):
+    t._epn_unit = True
+    return t
+
+
+def fwd_operands(feats=None, occupancy=False):
+    """Context manager for ONE conv forward whose input features are `feats`."""
+    ok = (not torch.is_grad_enabled() and _INFERENCE_OPERANDS == "f16" and
+          (occupancy or (feats is not None and getattr(feats, "_epn_unit", False))))
+    return ops.forward_operands("f16" if ok else "bf16")
+
+
 def norm_act(norm, x, act, residual=None, bias=None):
+    return _mark_unit(_norm_act(norm, x, act, residual, bias))
+
+
+def _norm_act(norm, x, act, residual=None, bias=None):
     """`act(norm(x + bias)) + residual` of the block wrappers (base_so3conv.py:55-57,119-125,209-211).  The two
     combinations every shipped model uses on CUDA -- InstanceNorm2d(affine=False) / training-mode BatchNorm2d followed
     by leaky_relu -- run as one fused library op; anything else goes through the torch modules.
@@ -49,11 +81,12 @@ def norm_act(norm, x, act, residual=None, bias=None):
     subtracts the per-channel mean, so a per-channel constant cancels exactly: the fused paths never add it (one
     full pass over the tensor saved; its gradient is identically zero) and only fold it into BatchNorm's running
     mean, which does see it."""
-    fusable = x.is_cuda and x.dtype == torch.float32 and act is F.leaky_relu and x.dim() == 4
+    fusable = x.is_cuda and x.dtype == torch.float32 and (act is F.leaky_relu or act is F.relu) and x.dim() == 4
+    slope = 0.01 if act is F.leaky_relu else 0.0    # F.leaky_relu's default slope; relu = slope 0
     if fusable and isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats:
-        return _NormActFn.apply(x, None, None, 0, norm.eps, 0.01, residual, bias)[0]
+        return _NormActFn.apply(x, None, None, 0, norm.eps, slope, residual, bias)[0]
     if fusable and isinstance(norm, nn.BatchNorm2d) and norm.training and norm.affine:
-        y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, 0.01, residual, bias)
+        y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, slope, residual, bias)
         if norm.track_running_stats:  # same bookkeeping as nn.BatchNorm2d.forward
             with torch.no_grad():
                 count = x.numel() // x.shape[1]
@@ -74,7 +107,7 @@ def norm_act(norm, x, act, residual=None, bias=None):
         # evaluation mode: per-channel affine map from the running statistics, one pass (no statistics kernels)
         mean = norm.running_mean if bias is None else norm.running_mean - bias.detach()
         stats = torch.stack((mean, torch.rsqrt(norm.running_var + norm.eps))).contiguous()
-        return ops.norm_act_fwd(x, norm.weight, norm.bias, 2, norm.eps, 0.01, residual, stats=stats)[0]
+        return ops.norm_act_fwd(x, norm.weight, norm.bias, 2, norm.eps, slope, residual, stats=stats)[0]
     if bias is not None:
         x = x + bias.view(1, -1, 1, 1)
     out = norm(x)
@@ -109,7 +142,8 @@ class IntraSO3ConvBlock(nn.Module):
         self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
 
     def forward(self, x):
-        x = self.conv(x)
+        with fwd_operands(x.feats):
+            x = self.conv(x)
         feat = norm_act(self.norm, x.feats, self.relu)
         if self.training and self.dropout is not None:
             feat = self.dropout(feat)
@@ -134,7 +168,9 @@ class InterSO3ConvBlock(nn.Module):
         self.dropout = nn.Dropout(dropout_rate) if dropout_rate > 0 else None
 
     def forward(self, x, inter_idx=None, inter_w=None):
-        inter_idx, inter_w, sample_idx, x = self.conv(x, inter_idx, inter_w)
+        occ = bool(getattr(x, "is_occupancy", False))
+        with fwd_operands(None if occ else x.feats, occupancy=occ):
+            inter_idx, inter_w, sample_idx, x = self.conv(x, inter_idx, inter_w)
         feat = norm_act(self.norm, x.feats, self.relu)
         if self.training and self.dropout is not None:
             feat = self.dropout(feat)
@@ -162,6 +198,7 @@ class SeparableSO3ConvBlock(nn.Module):
 
     def forward(self, x, inter_idx, inter_w):
         skip_feature = x.feats
+        skip_unit = bool(getattr(x, "is_occupancy", False)) or getattr(skip_feature, "_epn_unit", False)
         inter_idx, inter_w, sample_idx, x = self.inter_conv(x, inter_idx, inter_w)
         if self.use_intra:
             x = self.intra_conv(x)
@@ -173,7 +210,8 @@ class SeparableSO3ConvBlock(nn.Module):
         # 1x1 skip conv = a BasicSO3Conv with kernel size 1: run it through the library's fp32-faithful
         # channel GEMM (cuDNN would silently use TF32), parameters stay in nn.Conv2d for checkpoint parity
         w = self.skip_conv.weight.view(self.skip_conv.out_channels, self.skip_conv.in_channels)
-        skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w)
+        with fwd_operands(occupancy=skip_unit):   # a strided slice of a normalised activation is one too
+            skip_feature = sptk._BasicConvFn.apply(skip_feature.unsqueeze(2), w)
         # bias add, normalisation, activation and the residual add in one pass (see norm_act)
         feats = norm_act(self.norm, skip_feature, self.relu, residual=x.feats, bias=self.skip_conv.bias)
         x_out = sptk.SphericalPointCloud(x.xyz, feats, x.anchors)

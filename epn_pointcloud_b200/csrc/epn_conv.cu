@@ -17,6 +17,7 @@
 #include <atomic>
 
 #include "epn_internal.cuh"
+#include "epn_umma.cuh"
 
 namespace epn {
 
@@ -57,6 +58,12 @@ static bool inter_tiles_available(int c_in, int nn, int na, int ks) {
 }
 
 static std::atomic<size_t> g_slab_bytes{0};
+
+// Operand format of the forward GEMMs of the calling THREAD (epn_set_forward_operands): thread-local, so concurrent
+// callers (the reference's nn.DataParallel threads) cannot disturb each other.  Only forwards that keep no operand
+// tiles honour it (kept tiles feed the weight-gradient GEMM, whose gradient operand needs bf16's exponent range).
+static thread_local int t_fwd_fmt = 0;
+static int fwd_fmt() { return gemm_backend() == 0 ? t_fwd_fmt : 0; }
 
 static size_t slab_budget_bytes() {
     size_t v = g_slab_bytes.load();
@@ -170,14 +177,15 @@ struct ColsView {
 constexpr long long HUGE_Z = 1LL << 60;
 
 static int prep_weights(const float *W, int c_out, int ck, const Workspace &ws, bool fwd, bool transposed, cudaStream_t s,
-                        int kperm = 0, int step_layout = 0) {
+                        int kperm = 0, int step_layout = 0, int fmt = 0) {   // fmt: format of the FORWARD weight tiles
     if (gemm_backend() != 0) return 0;
     if (fwd && kperm) {
-        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), kperm, step_layout, s);
+        int rc = launch_inter_w_tiles_kperm(W, ws.tilesW, c_out, ck, umma_trb_for(c_out), kperm, step_layout, s, fmt);
         if (rc) return rc;
     } else if (fwd) {
         SplitSrc src{W, HUGE_Z, 0, ck, HUGE_Z, 0, 1};
-        int rc = launch_split_tiles(src, ws.tilesW, c_out, ck, umma_trb_for(c_out), s);
+        int rc = launch_split_tiles(src, ws.tilesW, c_out, ck, umma_trb_for(c_out), s, fmt,
+                                    fmt == umma::FMT_F16 ? umma::F16_W_SCALE : 1.0f);
         if (rc) return rc;
     }
     if (transposed) {
@@ -200,9 +208,9 @@ static int pick_split_k(int M, int N, long long K, int batch, int tile_m, int ti
 
 // out(c_out) = W . G with the activation operand already in ws.tilesA (rows = (z,j) columns, K = ck)
 static int gemm_fwd_tiles(const void *tilesA, int c_out, int ck, int bc, long long cols, ColsView out,
-                          const Workspace &ws, cudaStream_t s) {
+                          const Workspace &ws, cudaStream_t s, int fmt = 0) {
     GemmEpilogue ep{out.ptr, cols, out.stride_z, 1, out.stride_k, false};
-    return launch_umma_gemm(tilesA, ws.tilesW, (int)(bc * cols), c_out, ck, umma_trb_for(c_out), ep, 1, s);
+    return launch_umma_gemm(tilesA, ws.tilesW, (int)(bc * cols), c_out, ck, umma_trb_for(c_out), ep, 1, s, fmt);
 }
 
 // dW(c_out x ck) += dout . G with G = the forward operand tiles of this slab (rows = (z,j) columns, K = ck)
@@ -234,7 +242,7 @@ static int gemm_dw_tiles(ColsView dout, int c_out, int ck, int bc, long long col
 
 // out(c_out) = W . in(ck)
 static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long long cols, ColsView out,
-                    const Workspace &ws, cudaStream_t s) {
+                    const Workspace &ws, cudaStream_t s, int fmt = 0) {
     if (gemm_backend() != 0) {
         GemmOperand A{W, 0, ck, 1};
         GemmOperand B{in.ptr, in.stride_z, in.stride_k, 1};
@@ -242,9 +250,9 @@ static int gemm_fwd(const float *W, int c_out, int ck, ColsView in, int bc, long
     }
     const long long n = bc * cols;
     SplitSrc src{in.ptr, cols, in.stride_z, 1, HUGE_Z, 0, in.stride_k};
-    int rc = launch_split_tiles(src, ws.tilesA, n, ck, 128, s);
+    int rc = launch_split_tiles(src, ws.tilesA, n, ck, 128, s, fmt);
     if (rc) return rc;
-    return gemm_fwd_tiles(ws.tilesA, c_out, ck, bc, cols, out, ws, s);
+    return gemm_fwd_tiles(ws.tilesA, c_out, ck, bc, cols, out, ws, s, fmt);
 }
 
 // din(ck) = W^T . dout(c_out)
@@ -314,6 +322,8 @@ EPN_API size_t epn_get_slab_bytes(void) { return slab_budget_bytes(); }
 EPN_API void epn_set_gemm_backend(int simt) { g_backend.store(simt ? 1 : 0); }
 EPN_API int epn_get_gemm_backend(void) { return gemm_backend(); }
 EPN_API void epn_set_fused_inter(int on) { g_fused.store(on ? 1 : 0); }
+EPN_API void epn_set_forward_operands(int fmt) { t_fwd_fmt = fmt == umma::FMT_F16 ? umma::FMT_F16 : umma::FMT_BF16; }
+EPN_API int epn_get_forward_operands(void) { return t_fwd_fmt; }
 EPN_API int epn_get_fused_inter(void) { return fused_enabled(); }
 
 // ------------------------------------------------------------------ BasicSO3Conv
@@ -331,14 +341,15 @@ EPN_API int epn_basic_conv_fwd_f32(const float *x, const float *W, float *out, v
     const Workspace ws = carve(workspace, ck, co, (long long)sp.bc * sp.pc, false);
     EPN_CHECK_WS(ws.total);
     cudaStream_t s = as_stream(stream);
-    EPN_TRY(prep_weights(W, co, ck, ws, true, false, s));
+    const int fmt = fwd_fmt();
+    EPN_TRY(prep_weights(W, co, ck, ws, true, false, s, 0, 0, fmt));
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
         const int bc = b - b0 < sp.bc ? b - b0 : sp.bc;
         for (int j0 = 0; j0 < pa; j0 += sp.pc) {
             const long long cols = pa - j0 < sp.pc ? pa - j0 : sp.pc;
             ColsView in{const_cast<float *>(x) + (size_t)b0 * ck * pa + j0, (long long)ck * pa, pa};
             ColsView o{out + (size_t)b0 * co * pa + j0, (long long)co * pa, pa};
-            EPN_TRY(gemm_fwd(W, co, ck, in, bc, cols, o, ws, s));
+            EPN_TRY(gemm_fwd(W, co, ck, in, bc, cols, o, ws, s, fmt));
         }
     }
     return 0;
@@ -418,14 +429,17 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
         EPN_REQUIRE_PTR(grouped_layout);
         *grouped_layout = encode_layout(kperm, sp);
     }
-    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm, fused ? 1 : 0));
+    // fp16 operands (epn_set_forward_operands): inference forwards on the fused route and on the one-channel route
+    const bool occ_route = c_in == 1 && gemm_backend() == 0 && inter_group_occ_ok(c_in, nn, na, ks);
+    const int fmt = (grouped == nullptr && (fused || occ_route)) ? fwd_fmt() : 0;
+    EPN_TRY(prep_weights(W, c_out, ck, ws, true, false, s, kperm, fused ? 1 : 0, fmt));
     if (fused) {
         // kept tiles (training) keep the slab layout the weight-gradient pass expects
         InterGeom g{xyz, centers, anchors, kernels, sigma};
         const long long cols = (long long)p * na;
         const int rc = launch_inter_fused(feats, idx, g, ws.tilesW, out, (long long)c_out * p * na, (long long)p * na, keep,
                                           cdiv(ck, 32), cols, sp.bc, split_tiles_bytes((long long)sp.bc * cols, ck, 128), 0, p,
-                                          b, c_in, c_out, p_in, p, nn, na, ks, s);
+                                          b, c_in, c_out, p_in, p, nn, na, ks, s, fmt);
         return rc == 1 ? EPN_ERR_SHAPE : rc;
     }
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
@@ -439,9 +453,9 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             void *tiles = keep ? keep : ws.tilesA;  // kept tiles: every slab has its own region
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;  // 0: the grouping kernel wrote the operand tiles itself
-            if (c_in == 1 && gemm_backend() == 0 && inter_group_occ_ok(c_in, nn, na, ks)) {
+            if (occ_route) {
                 direct = launch_inter_group_occ(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cols, p0, pc, bc, p_in, p, nn, na,
-                                                ks, s);
+                                                ks, s, fmt);
                 if (direct != 0) return direct == 1 ? EPN_ERR_SHAPE : direct;
             } else if (kperm) {
                 direct = launch_inter_group_direct(feats_b, idx + (size_t)b0 * p * nn, g, tiles, cdiv(ck, 32), cols, p0, pc, bc,
@@ -454,7 +468,7 @@ EPN_API int epn_inter_so3conv_fwd_f32(const float *feats, const float *xyz, cons
             }
             EPN_REQUIRE(direct == 0 || grouped == nullptr, EPN_ERR_SHAPE, "grouped tiles requested for an unsupported shape");
             if (direct == 0) {
-                EPN_TRY(gemm_fwd_tiles(tiles, c_out, ck, bc, cols, o, ws, s));
+                EPN_TRY(gemm_fwd_tiles(tiles, c_out, ck, bc, cols, o, ws, s, occ_route ? fmt : 0));
             } else {
                 EPN_TRY(launch_inter_group_fwd(feats_b, idx + (size_t)b0 * p * nn, nullptr, g, ws.slab, cols, n_slab, p0, pc,
                                                bc, c_in, p_in, p, nn, na, ks, s));
@@ -589,7 +603,8 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
                 // out = sum_k Y_k permuted, reduced in shared memory -- the 12x larger grouped tensor never exists
                 const float *fz = feats + (size_t)b0 * c_in * p * na;
                 const int rc = launch_umma_intra_dx(fz, (long long)c_in * p * na, (long long)p * na, W, intra_idx,
-                                                    out + (size_t)b0 * c_out * p * na, ws.slab, ws.tilesA, bc, c_in, c_out, p, 1, s);
+                                                    out + (size_t)b0 * c_out * p * na, ws.slab, ws.tilesA, bc, c_in, c_out, p, 1, s,
+                                                    fwd_fmt());
                 if (rc == 0) continue;
                 if (rc != 1) return rc;
             }

@@ -25,7 +25,8 @@ using namespace umma;
 // contiguous in the source: every lane reads one full 32-byte sector, a warp 1 KB).
 template <bool K_LANES>
 __global__ void __launch_bounds__(256)
-split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int row_tiles, int k_blocks) {
+split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int row_tiles, int k_blocks, int fmt,
+                   float scale) {
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     const int x_idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (x_idx >= (K_LANES ? kcgs : rows_pad)) return;
@@ -47,7 +48,7 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
             }
         }
         uint4 hi, lo;
-        split8(x, hi, lo);
+        split8_fmt(x, hi, lo, fmt, scale);
         const int rt = row / tr, r = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
         uint8_t *tile = dst + ((size_t)rt * k_blocks + kb) * tile_bytes(tr);
         *reinterpret_cast<uint4 *>(tile + (size_t)kc * tr * 16 + (size_t)r * 16) = hi;
@@ -60,7 +61,7 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
 // the stores run along rows (32 lanes x 16 B = 512 contiguous bytes of the tile) instead of isolated 16-byte
 // pieces.
 __global__ void __launch_bounds__(256)
-split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int k_blocks) {
+split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int k_blocks, int fmt, float scale) {
     __shared__ uint4 s_hi[8][33], s_lo[8][33];
     const int tid = threadIdx.x;
     const int row0 = blockIdx.y * 32, kcg0 = blockIdx.x * 8;
@@ -82,7 +83,7 @@ split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, in
                 if (++kj == src.k_per_z) { kj = 0; ++kz; }
             }
         }
-        split8(x, s_hi[kq][r], s_lo[kq][r]);
+        split8_fmt(x, s_hi[kq][r], s_lo[kq][r], fmt, scale);
     }
     __syncthreads();
     {
@@ -102,21 +103,22 @@ size_t split_tiles_bytes(long long rows, long long K, int tr) {
     return (size_t)row_tiles * k_blocks * tile_bytes(tr);
 }
 
-int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s) {
+int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s, int fmt, float scale) {
     const int row_tiles = (int)((rows + tr - 1) / tr), k_blocks = (int)((K + KB - 1) / KB);
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     ProfScope prof(s, KC_SPLIT);
     if (src.stride_k == 1 && src.stride_row != 1 && (rows_pad + 31) / 32 <= 65535) {
         dim3 grid((kcgs + 7) / 8, (rows_pad + 31) / 32);
-        split_tiles_kcontig_kernel<<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, k_blocks);
+        split_tiles_kcontig_kernel<<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, k_blocks, fmt,
+                                                        scale);
     } else if (src.stride_k == 1 && src.stride_row != 1) {
         dim3 grid((kcgs + 255) / 256, rows_pad < 65535 ? rows_pad : 65535);
         split_tiles_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
-                                                      k_blocks);
+                                                      k_blocks, fmt, scale);
     } else {
         dim3 grid((rows_pad + 255) / 256, kcgs < 65535 ? kcgs : 65535);
         split_tiles_kernel<false><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
-                                                       k_blocks);
+                                                       k_blocks, fmt, scale);
     }
     return check_launch("split_tiles_kernel");
 }
@@ -136,6 +138,8 @@ struct UmmaGemmParams {
     const int32_t *intra_idx = nullptr;  // [60][12]
     float *dfeats = nullptr;             // [z][ch_total][pts_per_z][60]
     int ch_total = 0, pts_per_z = 0;
+    int fmt = 0;               // operand format of both tile arrays (FMT_BF16 / FMT_F16)
+    float out_scale = 1.0f;    // the accumulator is multiplied by this as it leaves TMEM (1 / F16_W_SCALE for FMT_F16)
 };
 
 __global__ void __launch_bounds__(192)
@@ -186,7 +190,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
         }
     } else if (warp_u == 5) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+        const uint32_t idesc = instr_desc_m128(p.trb, p.fmt);
         const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
         for (int i = 0; i < nkb; ++i) {
             const int s = i % p.stages;
@@ -238,6 +242,10 @@ umma_gemm_kernel(UmmaGemmParams p) {
                 for (int cc = 0; cc < gw; cc += 32) {
                     float v[32];
                     tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g0 + cc), v);
+                    if (p.out_scale != 1.0f) {
+                    #pragma unroll
+                        for (int jq = 0; jq < 32; ++jq) v[jq] *= p.out_scale;
+                    }
                     if (cc == 0 && g0 > 0) {  // the previous group's rows have left the staging buffer
                         bulk_wait_read0();
                         __syncwarp();
@@ -272,6 +280,10 @@ umma_gemm_kernel(UmmaGemmParams p) {
         for (int c0 = 0; c0 < p.trb; c0 += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+            if (p.out_scale != 1.0f) {
+            #pragma unroll
+                for (int jq = 0; jq < 32; ++jq) v[jq] *= p.out_scale;
+            }
             const long long colb = (long long)blockIdx.y * p.trb + c0;
             if (p.vec) {
                 // output columns are contiguous in memory: the thread's 32 values go out as 8 x 16 bytes
@@ -370,7 +382,7 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
         }
     } else if (warp_u == 5) {
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-        const uint32_t idesc = instr_desc_bf16_m128(p.trb);
+        const uint32_t idesc = instr_desc_m128(p.trb, p.fmt);
         const uint32_t a_lbo = TR_A * 16, b_lbo = (uint32_t)p.trb * 16;
         int it = 0, t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
@@ -440,6 +452,10 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                 for (int c0 = 0; c0 < 240; c0 += 32) {
                     float v[32];
                     tmem_ld_32x32(acc + (uint32_t)c0, v);
+                    if (p.out_scale != 1.0f) {
+                    #pragma unroll
+                        for (int jq = 0; jq < 32; ++jq) v[jq] *= p.out_scale;
+                    }
                     if (c0 + 32 >= 240) {  // accumulator fully read: hand it back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
@@ -481,6 +497,10 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                     for (int cc = 0; cc < gw; cc += 32) {
                         float v[32];
                         tmem_ld_32x32(acc + (uint32_t)(g0 + cc), v);
+                        if (p.out_scale != 1.0f) {
+                        #pragma unroll
+                            for (int jq = 0; jq < 32; ++jq) v[jq] *= p.out_scale;
+                        }
                         if (cc == 0) {  // the previous group's rows have left the staging buffer
                             bulk_wait_read0();
                             __syncwarp();
@@ -521,6 +541,10 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                 for (int c0 = 0; c0 < p.trb; c0 += 32) {
                     float v[32];
                     tmem_ld_32x32(acc + (uint32_t)c0, v);
+                    if (p.out_scale != 1.0f) {
+                    #pragma unroll
+                        for (int jq = 0; jq < 32; ++jq) v[jq] *= p.out_scale;
+                    }
                     if (c0 + 32 >= p.trb) {
                         tc_fence_before();
                         __syncwarp();
@@ -581,7 +605,7 @@ int umma_trb_for(int n_rows) {  // rows per B tile = UMMA N: multiple of 16, at 
 }
 
 int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
-                     const GemmEpilogue &ep, int split_k, cudaStream_t s) {
+                     const GemmEpilogue &ep, int split_k, cudaStream_t s, int fmt) {
     static DynSmemOnce once;
     if (int rc = ensure_dyn_smem(once, umma_gemm_kernel, 220 * 1024, "umma_gemm_kernel")) return rc;
     UmmaGemmParams p;
@@ -589,6 +613,8 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
     p.B = static_cast<const uint8_t *>(B_tiles);
     p.k_blocks = (int)((K + KB - 1) / KB);
     p.trb = trb;
+    p.fmt = fmt;
+    p.out_scale = fmt == FMT_F16 ? 1.0f / F16_W_SCALE : 1.0f;
     const size_t stage = tile_bytes(TR_A) + tile_bytes(trb);
     int stages = (int)((200 * 1024) / stage);
     if (stages > 4) stages = 4;
@@ -657,7 +683,7 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
 // (s_ch = 12, s_j = c_in*12); forward: ch = output channel, j = input channel (s_ch = c_in*12, s_j = 12).
 __global__ void __launch_bounds__(256)
 intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int n_ch, int n_j, long long s_ch,
-                      long long s_j, int k_blocks) {
+                      long long s_j, int k_blocks, int fmt, float scale) {
     const int rt = blockIdx.x, kcg = blockIdx.y * 2 + (threadIdx.x >> 7), r = threadIdx.x & 127;
     if (kcg >= k_blocks * (KB / 8)) return;
     const int cl = r / 12, k = r - cl * 12, ch = rt * 10 + cl;
@@ -668,7 +694,7 @@ intra_wt_tiles_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, in
         x[i] = (r < 120 && ch < n_ch && j < n_j) ? __ldg(W + (size_t)ch * s_ch + (size_t)j * s_j + k) : 0.f;
     }
     uint4 hi, lo;
-    split8(x, hi, lo);
+    split8_fmt(x, hi, lo, fmt, scale);
     uint8_t *tile = dst + ((size_t)rt * k_blocks + (kcg >> 2)) * tile_bytes(TR_A);
     *reinterpret_cast<uint4 *>(tile + (size_t)(kcg & 3) * TR_A * 16 + (size_t)r * 16) = hi;
     *reinterpret_cast<uint4 *>(tile + part_bytes(TR_A) + (size_t)(kcg & 3) * TR_A * 16 + (size_t)r * 16) = lo;
@@ -689,7 +715,7 @@ bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn) { return na == 6
 // grouped tensor (G resp. dG) only ever exists as one TMEM accumulator tile per SM.
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, int forward, cudaStream_t s) {
+                         int c_out, int p, int forward, cudaStream_t s, int fmt) {
     const long long n = (long long)bc * p * 60;
     if (!intra_dx_fused_ok(n, p, 60, 12) || n >= (1LL << 31)) return 1;
     const int c_rows = forward ? c_out : c_in, c_k = forward ? c_in : c_out;
@@ -699,12 +725,12 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
         dim3 grid(m_tiles, cdiv(k_blocks * (KB / 8), 2));
         intra_wt_tiles_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(wt_tiles), c_rows, c_k,
                                                    forward ? (long long)c_in * 12 : 12LL, forward ? 12LL : (long long)c_in * 12,
-                                                   k_blocks);
+                                                   k_blocks, fmt, fmt == FMT_F16 ? F16_W_SCALE : 1.0f);
         int rc = check_launch("intra_wt_tiles_kernel");
         if (rc) return rc;
     }
     SplitSrc src{dout, (long long)p * 60, dout_stride_z, 1, 1LL << 60, 0, dout_stride_o};
-    int rc = launch_split_tiles(src, dout_tiles, n, c_k, 240, s);
+    int rc = launch_split_tiles(src, dout_tiles, n, c_k, 240, s, fmt);
     if (rc) return rc;
     static DynSmemOnce once3;
     if (int rc3 = ensure_dyn_smem(once3, umma_gemm_persistent_kernel, 226 * 1024, "umma_gemm_persistent_kernel")) return rc3;
@@ -720,6 +746,8 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
     q.n_valid = (int)n;
     q.mode = 0; q.split_k = 1; q.vec = 0;
     q.ep_kind = forward ? 3 : 2;  // 3: the permutations themselves, 2: their inverses
+    q.fmt = fmt;
+    q.out_scale = fmt == FMT_F16 ? 1.0f / F16_W_SCALE : 1.0f;
     q.intra_idx = intra_idx;
     q.dfeats = dfeats;
     q.ch_total = c_rows;

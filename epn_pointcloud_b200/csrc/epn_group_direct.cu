@@ -469,7 +469,7 @@ inter_group_direct64_kernel(const float *__restrict__ feats, const int32_t *__re
 // SPConvNets/models/inv_so3net_pn.py:112-113).  Tiles: K = 24 in plain order, padded to one 32-wide block.
 __global__ void __launch_bounds__(GD_LANES * 3)
 inter_group_occ_kernel(const float *__restrict__ feats, const int32_t *__restrict__ idx, InterGeom g,
-                       uint8_t *__restrict__ tiles, long long cols_per_z, int p_in, int p, int nn, int p_off) {
+                       uint8_t *__restrict__ tiles, long long cols_per_z, int p_in, int p, int nn, int p_off, int fmt) {
     constexpr int NA = GD_NA, NTHR = GD_LANES * 3;
     __shared__ NeighbourList<DEDUP_MAX_RAW> L;
     const int tid = threadIdx.x;
@@ -509,7 +509,7 @@ inter_group_occ_kernel(const float *__restrict__ feats, const int32_t *__restric
     }
     if (!a_ok) return;
     uint4 hi, lo;
-    split8(acc, hi, lo);
+    split8_fmt(acc, hi, lo, fmt);
     const long long row = (long long)z * cols_per_z + (long long)pl * NA + aa;
     uint8_t *dst = tiles + (size_t)(row >> 7) * tile_bytes(TR_A) + (size_t)(row & 127) * 16 + (size_t)j * (TR_A * 16);
     *reinterpret_cast<uint4 *>(dst) = hi;
@@ -524,7 +524,7 @@ inter_group_occ_kernel(const float *__restrict__ feats, const int32_t *__restric
 // Weight tiles of the forward GEMM (rows = c_out in trb-row tiles) with K in the permuted order K'(c,k).
 __global__ void __launch_bounds__(256)
 inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, int c_out, int ck, int trb, int k_blocks,
-                           int mode, int steps) {
+                           int mode, int steps, int fmt, float scale) {
     const int row = blockIdx.x * 32 + (threadIdx.x & 31), kcg = blockIdx.y * 8 + (threadIdx.x >> 5);
     const int rows_pad = (c_out + trb - 1) / trb * trb;
     if (row >= rows_pad || kcg >= k_blocks * (KB / 8)) return;
@@ -535,7 +535,7 @@ inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ ds
         x[i] = (row < c_out && kp < ck) ? __ldg(W + (size_t)row * ck + inter_kperm_inv(kp, mode)) : 0.f;
     }
     uint4 hi, lo;
-    split8(x, hi, lo);
+    split8_fmt(x, hi, lo, fmt, scale);
     const int rt = row / trb, r = row - rt * trb;
     if (steps) {
         // "step" layout of the fused inter kernel (one row tile): every 16-wide k step is one contiguous block
@@ -550,11 +550,13 @@ inter_w_tiles_kperm_kernel(const float *__restrict__ W, uint8_t *__restrict__ ds
     *reinterpret_cast<uint4 *>(tile + part_bytes(trb) + (size_t)(kcg & 3) * trb * 16 + (size_t)r * 16) = lo;
 }
 
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s) {
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s,
+                               int fmt) {
     const int k_blocks = (ck + KB - 1) / KB, rows_pad = (c_out + trb - 1) / trb * trb;
     dim3 grid((rows_pad + 31) / 32, (k_blocks * (KB / 8) + 7) / 8);
     ProfScope prof(s, KC_SPLIT);
-    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks, mode, steps);
+    inter_w_tiles_kperm_kernel<<<grid, 256, 0, s>>>(W, static_cast<uint8_t *>(dst), c_out, ck, trb, k_blocks, mode, steps, fmt,
+                                                    fmt == FMT_F16 ? F16_W_SCALE : 1.0f);
     return check_launch("inter_w_tiles_kperm_kernel");
 }
 
@@ -601,12 +603,12 @@ int launch_inter_group_direct(const float *feats, const int32_t *idx, const Inte
 // One input channel (feats may be NULL = occupancy ones): tiles of one 32-wide K block in plain order.
 bool inter_group_occ_ok(int c, int nn, int na, int ks) { return c == 1 && ks == GD_KS && na == GD_NA && nn <= DEDUP_MAX_RAW; }
 int launch_inter_group_occ(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, long long cols_per_z,
-                           int p_off, int p_cnt, int bc, int p_in, int p, int nn, int na, int ks, cudaStream_t s) {
+                           int p_off, int p_cnt, int bc, int p_in, int p, int nn, int na, int ks, cudaStream_t s, int fmt) {
     if (!inter_group_occ_ok(1, nn, na, ks) || bc > 65535) return 1;
     dim3 grid(p_cnt, bc);
     ProfScope prof(s, KC_INTER_GROUP);
     inter_group_occ_kernel<<<grid, GD_LANES * 3, 0, s>>>(feats, idx, g, static_cast<uint8_t *>(tiles), cols_per_z, p_in, p, nn,
-                                                        p_off);
+                                                        p_off, fmt);
     return check_launch("inter_group_occ_kernel");
 }
 

@@ -62,7 +62,8 @@ struct FusedParams {
     long long keep_cols_per_z;
     size_t keep_slab_bytes;
     int c, c_out, p_in, p, nn, p_off, trb, nst, sps;   // sps: 16-k steps per weight-ring stage (1, 2 or 3)
-    uint32_t tmem_cols;
+    uint32_t tmem_cols;      // columns of ONE accumulator; the kernel allocates two (see acc_cross)
+    float out_scale;         // accumulator -> out factor (1 / F16_W_SCALE for fp16 operands, else 1)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -77,7 +78,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t
 //   1  one bulk copy per row, rows dealt round-robin to ALL threads of the point (a warp issues its lanes' copies
 //      one at a time, so spreading them shortens the slowest warp's issue phase)
 //   2  15 cp.async of 16 bytes per row by all threads + mbarrier arrive.noinc
-template <int MODE, int GATHER>
+// FMT: operand format of the A pieces and the weight tiles (epn_umma.cuh: FMT_BF16, or FMT_F16 for inference forwards)
+template <int MODE, int GATHER, int FMT>
 __global__ void __launch_bounds__(FuCfg<MODE>::PTS *FU_LANES *(FU_KS / FuCfg<MODE>::KG) + FU_CTRL, 1)  // 480 + 32
 inter_fused_kernel(FusedParams P) {
     using C = FuCfg<MODE>;
@@ -137,7 +139,12 @@ inter_fused_kernel(FusedParams P) {
         mbar_init(smem_u32(&s_accum), 1);
         fence_barrier_init();
     }
-    if (warp == NPWARPS) tmem_alloc(smem_u32(&s_tmem), P.tmem_cols);
+    // Two fp32 accumulators in TMEM: the hi*hi products go to the first, the two cross products (hi*lo, lo*hi, ~2^-9 /
+    // 2^-11 of the former) to the second, and the epilogue adds them.  The tensor core TRUNCATES the accumulator after
+    // every MMA (measured: the error of a K-long contraction grows linearly with the number of MMAs, 6e-6 at K = 1536,
+    // 1.2e-5 at K = 3072, against 4e-7 at K = 64); a small addend costs the big accumulator as much as a large one, so
+    // keeping the cross terms apart removes two of the three truncations per k step from the sum that matters.
+    if (warp == NPWARPS) tmem_alloc(smem_u32(&s_tmem), 2 * P.tmem_cols);
 
     // ---- distinct neighbours of the PTS points: DW whole warps per point do the work, every thread of the CTA takes
     //      part in the three barriers of dedup_row
@@ -171,6 +178,7 @@ inter_fused_kernel(FusedParams P) {
         // as soon as a non-blocking test shows that the MMAs that read it have completed (blocking only when the
         // stage about to be consumed has not been requested yet), so up to nst - 1 loads stay in flight.
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t tmem_x = tmem_u + P.tmem_cols;   // accumulator of the cross terms
         const uint32_t sps = (uint32_t)P.sps;                      // 16-k steps per ring stage (divides STEPS_G)
         const int stages_g = STEPS_G / (int)sps;                   // ring stages per granule
         const int total_stages = total_gran * stages_g, stages_pass = ngran * stages_g;
@@ -191,7 +199,7 @@ inter_fused_kernel(FusedParams P) {
             ++loaded;
         };
         const uint32_t half_bytes = (uint32_t)P.trb * 32u;
-        const uint32_t idesc = instr_desc_bf16_m128(P.trb);
+        const uint32_t idesc = instr_desc_m128(P.trb, FMT);
         const uint32_t b_lbo = (uint32_t)P.trb * 16u;
         const uint64_t a_desc0 = smem_desc(smem_u32(a_tiles), A_LBO, 128);      // + (byte offset >> 4)
         const uint64_t b_desc0 = smem_desc(ring_u32, b_lbo, 128);
@@ -221,9 +229,9 @@ inter_fused_kernel(FusedParams P) {
                 const uint64_t b_hi = b_desc0 + (uint64_t)(slot * stage16 + sub * step16);
                 const uint64_t b_lo = b_hi + (uint64_t)half16;
                 mma_bf16_ss_elect(tmem_u, a_hi, b_hi, idesc, accumulate);
+                mma_bf16_ss_elect(tmem_x, a_hi, b_lo, idesc, accumulate);
                 accumulate = 1;
-                mma_bf16_ss_elect(tmem_u, a_hi, b_lo, idesc, 1);
-                mma_bf16_ss_elect(tmem_u, a_lo, b_hi, idesc, 1);
+                mma_bf16_ss_elect(tmem_x, a_lo, b_hi, idesc, 1);
                 if (++sub == sps) {
                     sub = 0;
                     mma_commit_elect(wempty0 + 8u * slot);   // the slot may be refilled once these MMAs have read it
@@ -395,12 +403,7 @@ inter_fused_kernel(FusedParams P) {
                                 float e0, o0, e1, o1;
                                 unpack_f32x2(acc2[2 * ip], e0, o0);
                                 unpack_f32x2(acc2[2 * ip + 1], e1, o1);
-                                const float v0 = e0 + o0, v1 = e1 + o1;
-                                const __nv_bfloat162 hp = __floats2bfloat162_rn(v0, v1);
-                                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
-                                const __nv_bfloat162 lp = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
-                                hi[cl4 * 3 + ip] = hb;
-                                lo[cl4 * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                                split2<FMT>(e0 + o0, e1 + o1, hi[cl4 * 3 + ip], lo[cl4 * 3 + ip]);
                             }
                             if (cl4 >= 1) {  // 6 (cl4 + 1) values so far: piece j = cl4 - 1 (values 8j .. 8j+7) is complete
                                 const int jj = cl4 - 1;
@@ -443,12 +446,7 @@ inter_fused_kernel(FusedParams P) {
                                 }
 #pragma unroll
                             for (int ip = 0; ip < 3; ++ip) {
-                                const __nv_bfloat162 hp = __floats2bfloat162_rn(v[2 * ip], v[2 * ip + 1]);
-                                const uint32_t hb = *reinterpret_cast<const uint32_t *>(&hp);
-                                const __nv_bfloat162 lp = __floats2bfloat162_rn(v[2 * ip] - __uint_as_float(hb << 16),
-                                                                                v[2 * ip + 1] - __uint_as_float(hb & 0xffff0000u));
-                                hi[h * 6 + cp * 3 + ip] = hb;
-                                lo[h * 6 + cp * 3 + ip] = *reinterpret_cast<const uint32_t *>(&lp);
+                                split2<FMT>(v[2 * ip], v[2 * ip + 1], hi[h * 6 + cp * 3 + ip], lo[h * 6 + cp * 3 + ip]);
                             }
                         }
                         const int kcl0 = grp * 3, kc0 = g * 24 + grp * 3;
@@ -485,7 +483,7 @@ inter_fused_kernel(FusedParams P) {
                 const int cg = cg0 + (warp >> 2);
                 const bool active = cg * 32 < P.c_out;   // uniform over the four warps that share a staging area
                 float v[32];
-                if (active) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), v);
+                if (active) tmem_ld_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), P.tmem_cols, v);
                 if (active && rpt == 1) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) stage[jj * 64 + ra] = v[jj];
@@ -495,7 +493,7 @@ inter_fused_kernel(FusedParams P) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
                         const int o = cg * 32 + jj;
-                        if (o < P.c_out) orow[(size_t)o * P.out_so] = v[jj] + stage[jj * 64 + ra];
+                        if (o < P.c_out) orow[(size_t)o * P.out_so] = (v[jj] + stage[jj * 64 + ra]) * P.out_scale;
                     }
                 }
                 __syncthreads();
@@ -504,12 +502,12 @@ inter_fused_kernel(FusedParams P) {
             float *orow = P.out + (size_t)z * P.out_sz + (size_t)(blockIdx.x * PTS + rpt) * NA + ra;
             for (int cg = warp >> 2; cg * 32 < P.c_out; cg += NWARPS / 4) {
                 float v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), v);
+                tmem_ld_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), P.tmem_cols, v);
                 if (ra < NA) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
                         const int o = cg * 32 + jj;
-                        if (o < P.c_out) orow[(size_t)o * P.out_so] = v[jj];
+                        if (o < P.c_out) orow[(size_t)o * P.out_so] = v[jj] * P.out_scale;
                     }
                 }
             }
@@ -519,11 +517,11 @@ inter_fused_kernel(FusedParams P) {
     __syncthreads();
     if (warp == NPWARPS) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, P.tmem_cols);
+        tmem_dealloc(tmem_base, 2 * P.tmem_cols);
     }
 }
 
-template <int MODE, int GATHER>
+template <int MODE, int GATHER, int FMT = 0>
 int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     using C = FuCfg<MODE>;
     constexpr int NPROD = C::PTS * FU_LANES * (FU_KS / C::KG);
@@ -545,9 +543,9 @@ int launch_fused_variant(FusedParams &P, int p_cnt, int bc, cudaStream_t s) {
     P.nst = nst;
     const size_t smem_bytes = fixed + (size_t)nst * stage;
     static DynSmemOnce once;  // one per template instantiation
-    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE, GATHER>, (int)budget, "inter_fused_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once, inter_fused_kernel<MODE, GATHER, FMT>, (int)budget, "inter_fused_kernel")) return rc;
     dim3 grid(MODE == 3 ? p_cnt : p_cnt / C::PTS, bc);
-    inter_fused_kernel<MODE, GATHER><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
+    inter_fused_kernel<MODE, GATHER, FMT><<<grid, NPROD + FU_CTRL, smem_bytes, s>>>(P);
     return check_launch("inter_fused_kernel");
 }
 
@@ -575,8 +573,9 @@ int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool k
 int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &g, const void *w_tiles, float *out,
                        long long out_stride_z, long long out_stride_o, void *keep_tiles, int keep_k_blocks,
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt, int bc, int c, int c_out, int p_in, int p, int nn,
-                       int na, int ks, cudaStream_t s) {
+                       int na, int ks, cudaStream_t s, int fmt) {
     const int mode = inter_fused_mode(c, c_out, p_cnt, nn, na, ks, keep_tiles != nullptr);
+    if (fmt == FMT_F16 && keep_tiles != nullptr) return 1;   // kept tiles are bf16 (the weight-gradient GEMM's format)
     if (mode == 0 || bc > 65535 || feats == nullptr) return 1;
     FusedParams P;
     P.feats = feats;
@@ -596,7 +595,13 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
     uint32_t cols = 32;
     while ((int)cols < P.trb) cols *= 2;
     P.tmem_cols = cols;
+    P.out_scale = fmt == FMT_F16 ? 1.0f / F16_W_SCALE : 1.0f;
     ProfScope prof(s, KC_INTER_FUSED);
+    if (fmt == FMT_F16) {   // inference forward with fp16 operands: default gather variant only
+        if (mode == 1 && (nn > 16 || p_cnt % 2 != 0)) return launch_fused_variant<3, 1, FMT_F16>(P, p_cnt, bc, s);
+        if (mode == 1) return launch_fused_variant<1, 1, FMT_F16>(P, p_cnt, bc, s);
+        return launch_fused_variant<2, 1, FMT_F16>(P, p_cnt, bc, s);
+    }
     int gather = 1;
     if (const char *e = getenv("EPN_FU_GATHER")) gather = atoi(e);   // tuning knob (tools/fused_sweep.py)
     if (mode == 1 && (nn > 16 || p_cnt % 2 != 0)) {   // halves variant (inference only, see inter_fused_mode)

@@ -122,7 +122,7 @@ int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool k
 int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &g, const void *w_tiles, float *out,
                        long long out_stride_z, long long out_stride_o, void *keep_tiles, int keep_k_blocks,
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt,
-                       int bc, int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
+                       int bc, int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s, int fmt = 0);
 
 // epn_group_direct.cu -- inter grouping with the bf16 split in registers; the operand tiles use a permuted K order
 // (24 kernel points):  mode 1 (K <= 16 neighbours, c % 4 == 0)  K'(c,k) = (c/4)*96  + (k/6)*24 + (c%4)*6 + (k%6)
@@ -140,11 +140,12 @@ int launch_inter_group_direct(const float *feats, const int32_t *idx, const Inte
                               long long cols_per_z, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn, int na,
                               int ks, cudaStream_t s);
 // steps = 1: the fused kernel's layout (every 16-k step contiguous, c_out <= 256) instead of split tiles
-int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s);
+int launch_inter_w_tiles_kperm(const float *W, void *dst, int c_out, int ck, int trb, int mode, int steps, cudaStream_t s,
+                               int fmt = 0);
 // one input channel (feats NULL = occupancy ones), any row length up to 128: tiles of one K block in plain order
 bool inter_group_occ_ok(int c, int nn, int na, int ks);
 int launch_inter_group_occ(const float *feats, const int32_t *idx, const InterGeom &g, void *tiles, long long cols_per_z,
-                           int p_off, int p_cnt, int bc, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
+                           int p_off, int p_cnt, int bc, int p_in, int p, int nn, int na, int ks, cudaStream_t s, int fmt = 0);
 
 // epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
@@ -173,11 +174,13 @@ struct GemmEpilogue {
     long long cols_per_z = 1LL << 60, stride_cz = 0;
 };
 size_t split_tiles_bytes(long long rows, long long K, int tr);
-int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s);
+// fmt / scale: operand format of the tiles (epn_umma.cuh FMT_*) and an exact power-of-two factor applied first
+int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long K, int tr, cudaStream_t s, int fmt = 0,
+                       float scale = 1.0f);
 int umma_trb_for(int n_rows);
 // D[m_rows, n_rows] = A[m_rows, K] * B[n_rows, K]^T on split tiles (A: 128-row tiles, B: trb-row tiles)
 int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n_rows, long long K, int trb,
-                     const GemmEpilogue &ep, int split_k, cudaStream_t s);
+                     const GemmEpilogue &ep, int split_k, cudaStream_t s, int fmt = 0);
 
 // Intra conv data gradient with the inverse-permutation reduction fused into the GEMM epilogue (epn_gemm_umma.cu);
 // returns 1 if the shape is unsupported.
@@ -186,7 +189,7 @@ size_t intra_dx_dout_bytes(long long n, int c_k);
 bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn);
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, int forward, cudaStream_t s);
+                         int c_out, int p, int forward, cudaStream_t s, int fmt = 0);
 
 // epn_gemm_dw.cu -- dW[c_out, ck] += dout . G straight from the forward operand tiles of a slab
 // (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles

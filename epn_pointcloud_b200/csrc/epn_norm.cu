@@ -27,55 +27,71 @@ __device__ __forceinline__ float block_sum(float v, float *s_red) {
     return __shfl_sync(0xffffffffu, t, 0);
 }
 
-// part[row] = (mean, M2) of row (b,c)
+__device__ __forceinline__ double block_sum_d(double v, double *s_red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double t = (lane < NT / 32) ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+
+// part[row] = (mean, M2) of row (b,c), accumulated in fp64 (the kernel is HBM-bound: ~24 bytes per SM and cycle need
+// 6 fp64 adds per cycle of the 64 an SM has): a row that is CONSTANT (block 0 of every shipped model: the skip
+// convolution of the all-ones occupancy features, base_so3conv.py:206-211) must come out with mean == the constant
+// and M2 == 0 exactly -- with an fp32 mean one ulp off, (x - mean) / sqrt(0 + eps) turns that ulp into a 1e-5 error.
 __global__ void __launch_bounds__(NT)
-norm_row_stats_kernel(const float *__restrict__ x, float2 *__restrict__ part, int n) {
-    __shared__ float s_red[NT / 32];
+norm_row_stats_kernel(const float *__restrict__ x, double2 *__restrict__ part, int n) {
+    __shared__ double s_red[NT / 32];
     const float *row = x + (size_t)blockIdx.x * n;
     const int n4 = (n % 4 == 0) ? n / 4 : 0;
-    float s = 0.f;
+    double s = 0.0;
     for (int i = threadIdx.x; i < n4; i += NT) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + i);
-        s += (v.x + v.y) + (v.z + v.w);
+        s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
     }
-    for (int i = n4 * 4 + threadIdx.x; i < n; i += NT) s += __ldg(row + i);
-    const float mean = block_sum(s, s_red) / (float)n;
-    float m2 = 0.f;
+    for (int i = n4 * 4 + threadIdx.x; i < n; i += NT) s += (double)__ldg(row + i);
+    const double mean_d = block_sum_d(s, s_red) / (double)n;
+    double m2 = 0.0;
     for (int i = threadIdx.x; i < n4; i += NT) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + i);
-        const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+        const double a = (double)v.x - mean_d, b = (double)v.y - mean_d, c = (double)v.z - mean_d, d = (double)v.w - mean_d;
         m2 += (a * a + b * b) + (c * c + d * d);
     }
     for (int i = n4 * 4 + threadIdx.x; i < n; i += NT) {
-        const float a = __ldg(row + i) - mean;
+        const double a = (double)__ldg(row + i) - mean_d;
         m2 += a * a;
     }
-    m2 = block_sum(m2, s_red);
-    if (threadIdx.x == 0) part[blockIdx.x] = make_float2(mean, m2);
+    m2 = block_sum_d(m2, s_red);
+    if (threadIdx.x == 0) part[blockIdx.x] = make_double2(mean_d, m2 > 0.0 ? m2 : 0.0);
 }
 
-// stats[g] = mean, stats[G + g] = rstd.  mode 0: g = row.  mode 1: g = channel, combined over the batch.
-__global__ void norm_finalize_kernel(const float2 *__restrict__ part, float *__restrict__ stats, int b, int c, int n,
+// stats[g] = mean, stats[G + g] = rstd.  mode 0: g = row.  mode 1: g = channel, combined over the batch (fp64).
+__global__ void norm_finalize_kernel(const double2 *__restrict__ part, float *__restrict__ stats, int b, int c, int n,
                                      int mode, float eps) {
     const int G = mode == 0 ? b * c : c;
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= G) return;
     if (mode == 0) {
-        const float2 p = part[gi];
-        stats[gi] = p.x;
-        stats[G + gi] = rsqrtf(p.y / (float)n + eps);
+        const double2 p = part[gi];
+        stats[gi] = (float)p.x;
+        stats[G + gi] = (float)(1.0 / sqrt(p.y / (double)n + (double)eps));
     } else {
-        float mean = 0.f;
+        double mean = 0.0;
         for (int bi = 0; bi < b; ++bi) mean += part[bi * c + gi].x;
-        mean /= (float)b;
-        float m2 = 0.f;
+        mean /= (double)b;
+        double m2 = 0.0;
         for (int bi = 0; bi < b; ++bi) {
-            const float2 p = part[bi * c + gi];
-            const float d = p.x - mean;
-            m2 += p.y + (float)n * d * d;
+            const double2 p = part[bi * c + gi];
+            const double d = p.x - mean;
+            m2 += p.y + (double)n * d * d;
         }
-        stats[gi] = mean;
-        stats[G + gi] = rsqrtf(m2 / ((float)b * (float)n) + eps);
+        stats[gi] = (float)mean;
+        stats[G + gi] = (float)(1.0 / sqrt(m2 / ((double)b * (double)n) + (double)eps));
     }
 }
 
@@ -90,7 +106,9 @@ norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, 
     const int gi = mode == 0 ? rowi : ch;
     const float mean = stats[gi], rstd = stats[G + gi];
     const float ga = gamma ? gamma[ch] : 1.f, be = beta ? beta[ch] : 0.f;
-    const float sc = rstd * ga, sh = be - mean * sc;
+    // (x - mean) * sc + beta, NOT x * sc + (beta - mean * sc): the subtraction first is exact for values near the mean,
+    // the folded form loses |mean| * sc * 2^-24 (a constant row would come out as beta + noise instead of beta)
+    const float sc = rstd * ga;
     const float *row = x + (size_t)rowi * n;
     const float *res = residual ? residual + (size_t)rowi * n : nullptr;   // skip connection: y = act(norm(x)) + residual
     float *out = y + (size_t)rowi * n;
@@ -98,10 +116,10 @@ norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, 
         for (int i = blockIdx.x * NT + threadIdx.x; i < n / 4; i += gridDim.x * NT) {
             const float4 v = __ldg(reinterpret_cast<const float4 *>(row) + i);
             float4 r;
-            r.x = lrelu(fmaf(v.x, sc, sh), slope);
-            r.y = lrelu(fmaf(v.y, sc, sh), slope);
-            r.z = lrelu(fmaf(v.z, sc, sh), slope);
-            r.w = lrelu(fmaf(v.w, sc, sh), slope);
+            r.x = lrelu(fmaf(v.x - mean, sc, be), slope);
+            r.y = lrelu(fmaf(v.y - mean, sc, be), slope);
+            r.z = lrelu(fmaf(v.z - mean, sc, be), slope);
+            r.w = lrelu(fmaf(v.w - mean, sc, be), slope);
             if (res != nullptr) {
                 const float4 q = __ldg(reinterpret_cast<const float4 *>(res) + i);
                 r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w;
@@ -110,7 +128,7 @@ norm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gamma, 
         }
     } else {
         for (int i = blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT)
-            out[i] = lrelu(fmaf(row[i], sc, sh), slope) + (res ? res[i] : 0.f);
+            out[i] = lrelu(fmaf(row[i] - mean, sc, be), slope) + (res ? res[i] : 0.f);
     }
 }
 
@@ -207,7 +225,7 @@ EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float
     EPN_REQUIRE(workspace_bytes >= epn_norm_act_workspace_bytes(b, c), EPN_ERR_WORKSPACE, "workspace too small");
     EPN_REQUIRE((((uintptr_t)x | (uintptr_t)y | (uintptr_t)residual) & 15) == 0, EPN_ERR_ALIGN, "x, y and residual must be 16-byte aligned");
     cudaStream_t s = as_stream(stream);
-    float2 *part = static_cast<float2 *>(workspace);
+    double2 *part = static_cast<double2 *>(workspace);   // rows x 16 bytes = the first half of the workspace
     const int rows = b * c, G = mode == 0 ? rows : c;
     ProfScope prof(s, KC_NORM);
     int rc = 0;

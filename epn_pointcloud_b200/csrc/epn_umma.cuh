@@ -12,6 +12,7 @@
 //   (three kind::f16 MMAs per 16-wide k step, fp32 accumulation in TMEM, error ~1e-5 relative).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace epn {
@@ -122,6 +123,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 __host__ __device__ constexpr uint32_t instr_desc_bf16_m128(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// Operand format of the split tiles.  FMT_BF16 (default everywhere): hi/lo are bf16 -- fp32's exponent range, 16
+// significand bits (2^-18 relative per operand).  FMT_F16 (inference forwards that ask for it, see
+// epn_set_forward_operands): hi/lo are fp16 -- 22 significand bits where |x| >= 2^-3 (below that the lo part is
+// subnormal: absolute error <= 2^-25), at the same MMA rate and the same bytes, but only fp16's range (|x| > 65504
+// becomes inf and the result NaN: loud, not silently wrong).  Weights are multiplied by the exact power of two
+// F16_W_SCALE before the split (|W| >= 1.2e-4 then has a normal lo part; |W| < 64 is required) and the epilogue
+// multiplies the accumulator by 1 / F16_W_SCALE.
+enum { FMT_BF16 = 0, FMT_F16 = 1 };
+constexpr float F16_W_SCALE = 1024.0f;
+// same descriptor with A = B = F16 (format code 0) when fmt == FMT_F16
+__host__ __device__ constexpr uint32_t instr_desc_m128(int n, int fmt) {
+    return (1u << 4) | (fmt == FMT_F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -207,6 +221,15 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// main accumulator + cross-term accumulator `cross_cols` columns further on (see epn_inter_fused.cu): v = main + cross
+__device__ __forceinline__ void tmem_ld_sum2(uint32_t taddr, uint32_t cross_cols, float (&v)[32]) {
+    float x[32];
+    tmem_ld_32x32(taddr, v);
+    tmem_ld_32x32(taddr + cross_cols, x);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += x[i];
+}
+
 // ---------------------------------------------------------------- bf16 hi/lo split
 // x ~= hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); returns 8 elements as two 16-byte chunks.
 __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo) {
@@ -222,6 +245,38 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4 &hi, uint4 &lo
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// fp16 hi/lo split of two values (low half = v0): hi = f16_rn(v), lo = f16_rn(v - hi)
+__device__ __forceinline__ void split2_f16(float v0, float v1, uint32_t &h, uint32_t &l) {
+    const __half2 hp = __floats2half2_rn(v0, v1);
+    const float2 hf = __half22float2(hp);
+    const __half2 lp = __floats2half2_rn(v0 - hf.x, v1 - hf.y);
+    h = *reinterpret_cast<const uint32_t *>(&hp);
+    l = *reinterpret_cast<const uint32_t *>(&lp);
+}
+__device__ __forceinline__ void split2_bf16(float v0, float v1, uint32_t &h, uint32_t &l) {
+    const __nv_bfloat162 hp = __floats2bfloat162_rn(v0, v1);
+    h = *reinterpret_cast<const uint32_t *>(&hp);
+    const __nv_bfloat162 lp = __floats2bfloat162_rn(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xffff0000u));
+    l = *reinterpret_cast<const uint32_t *>(&lp);
+}
+template <int FMT>
+__device__ __forceinline__ void split2(float v0, float v1, uint32_t &h, uint32_t &l) {
+    if (FMT == FMT_F16) split2_f16(v0, v1, h, l);
+    else split2_bf16(v0, v1, h, l);
+}
+// 8 elements in the format chosen at run time (`scale`: exact power of two applied first -- F16_W_SCALE for weights)
+__device__ __forceinline__ void split8_fmt(const float (&x)[8], uint4 &hi, uint4 &lo, int fmt, float scale = 1.0f) {
+    if (fmt == FMT_F16) {
+        uint32_t h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2_f16(x[2 * i] * scale, x[2 * i + 1] * scale, h[i], l[i]);
+        hi = make_uint4(h[0], h[1], h[2], h[3]);
+        lo = make_uint4(l[0], l[1], l[2], l[3]);
+    } else {
+        split8(x, hi, lo);
+    }
 }
 
 }  // namespace umma

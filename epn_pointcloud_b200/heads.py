@@ -15,15 +15,16 @@ import torch.nn.functional as F
 
 from . import functional as L
 from . import modules as sptk
-from .blocks import BasicSO3ConvBlock, backbone_params, cls_backbone_params, preprocess_input
+from .blocks import BasicSO3ConvBlock, backbone_params, cls_backbone_params, fwd_operands, norm_act, preprocess_input
 
 
-def conv1x1(conv, x):
+def conv1x1(conv, x, add_bias=True):
     """nn.Conv2d(c_in, c_out, 1) applied to x [b, c_in, p, a] through the library GEMM (parameters stay in
-    the nn.Conv2d so checkpoints keep their keys)."""
+    the nn.Conv2d so checkpoints keep their keys).  add_bias=False leaves the bias to a following norm_act."""
     w = conv.weight.view(conv.out_channels, conv.in_channels)
-    y = sptk._BasicConvFn.apply(x.contiguous().unsqueeze(2), w)
-    return y if conv.bias is None else y + conv.bias.view(1, -1, 1, 1)
+    with fwd_operands(x):
+        y = sptk._BasicConvFn.apply(x.contiguous().unsqueeze(2), w)
+    return y if (conv.bias is None or not add_bias) else y + conv.bias.view(1, -1, 1, 1)
 
 
 class PointnetSO3Conv(nn.Module):
@@ -80,7 +81,8 @@ class ClsOutBlockPointnet(nn.Module):
             return x_out[:, :40].mean(-1).mean(-1), None
         norm_cnt = 0
         for linear in self.linear:
-            x_out = F.relu(self.norm[norm_cnt](conv1x1(linear, x_out)))
+            # conv bias + BatchNorm2d + relu as one fused pass (blocks.norm_act; the bias cancels in the batch statistics)
+            x_out = norm_act(self.norm[norm_cnt], conv1x1(linear, x_out, add_bias=False), F.relu, bias=linear.bias)
             norm_cnt += 1
         out_feat = x_out
         x_out = self.pointnet(sptk.SphericalPointCloud(x.xyz, out_feat, x.anchors))

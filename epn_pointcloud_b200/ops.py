@@ -9,6 +9,7 @@ order and return shapes of the reference's pybind modules `vgtk.cuda.grouping`
 (gathering_cuda.cpp:61-65) and `vgtk.cuda.zpconv` (zpconv_cuda.cpp:112-118).
 """
 import ctypes
+import contextlib
 import types
 
 import torch
@@ -479,8 +480,22 @@ def set_gemm_backend(name):
 
 
 def set_fused_inter(on):
-    """True: InterSO3Conv forward runs as ONE fused kernel; False (default): grouping kernel + GEMM kernel."""
+    """True (default): InterSO3Conv forward runs as ONE fused kernel; False: grouping kernel + GEMM kernel."""
     _lib.lib().epn_set_fused_inter(1 if on else 0)
+
+
+@contextlib.contextmanager
+def forward_operands(fmt):
+    """Operand format of the forward GEMMs issued by THIS thread inside the block: 'bf16' (default: fp32's range,
+    ~2^-18 per operand) or 'f16' (22 significand bits at the same speed, fp16's range: for inputs known to be
+    normalised activations; honoured only by forwards that keep no operand tiles).  See include/epn_b200.h."""
+    L = _lib.lib()
+    old = L.epn_get_forward_operands()
+    L.epn_set_forward_operands({"bf16": 0, "f16": 1}[fmt])
+    try:
+        yield
+    finally:
+        L.epn_set_forward_operands(old)
 
 
 # ------------------------------------------ drop-in namespaces for vgtk.cuda.*

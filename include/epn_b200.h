@@ -235,13 +235,26 @@ void epn_set_gemm_backend(int simt);
 void epn_set_slab_bytes(size_t bytes);
 size_t epn_get_slab_bytes(void);
 int epn_get_gemm_backend(void);
-/* InterSO3Conv forward schedule on the tensor-core engine: 0 (default) = grouping kernel writing operand tiles
- * followed by the GEMM kernel; 1 (or EPN_FUSED=1) = ONE fused kernel (gather + kernel weights + spatial
- * contraction feeding the channel GEMM from shared memory; replaces the op chain
- * vgtk/vgtk/so3conv/functional.py:118-218 -> spconv/functional.py:361-390 -> so3conv/modules.py:48-55).
- * Both give the same results (tests); the two-kernel schedule is the faster one on the B200 today. */
+/* InterSO3Conv forward schedule on the tensor-core engine: 1 (default) = ONE fused kernel (gather + kernel weights +
+ * spatial contraction feeding the channel GEMM from shared memory; replaces the op chain
+ * vgtk/vgtk/so3conv/functional.py:118-218 -> spconv/functional.py:361-390 -> so3conv/modules.py:48-55);
+ * 0 (or EPN_FUSED=0) = grouping kernel writing operand tiles followed by the GEMM kernel.  Same results (tests). */
 void epn_set_fused_inter(int on);
 int epn_get_fused_inter(void);
+
+/* ------------------------------------------------ operand format of the forward GEMMs (THREAD-LOCAL)
+ * 0 (default) = bf16 hi/lo split operands: fp32's exponent range, ~2^-18 relative per operand.
+ * 1           = fp16 hi/lo split operands for the forwards of the CALLING THREAD that keep no operand tiles
+ *               (grouped == NULL: inference; BasicSO3Conv forwards always): 22 significand bits at the same speed,
+ *               but fp16's RANGE -- activations must satisfy |x| * (neighbours per row) < 65504 (beyond that the
+ *               output is NaN, never silently wrong), are resolved to 2^-25 absolute below 2^-3, and weights
+ *               need 1e-6 < |W| < 64 to keep their precision (they are scaled by 2^10 internally).  Meant for
+ *               callers that know their inputs are normalised activations: the block wrappers of this package set
+ *               it for the convs that follow their own norm + activation under torch.no_grad().
+ * The setting is per host thread (threads of nn.DataParallel do not disturb each other) and is read at the
+ * start of each forward call. */
+void epn_set_forward_operands(int fmt);
+int epn_get_forward_operands(void);
 
 #ifdef __cplusplus
 }

@@ -206,6 +206,67 @@ def test_sweep_shape_16k_points_vs_c_oracle(E, O):
     assert rel_err(y.feats[:, :, win], ref) < FEAT_TOL
 
 
+# ------------------------------------------------------------ fp16 hi/lo operands of inference forwards
+@pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,radius,sigma", [
+    (64, 64, 512, 1, 16, 0.2828, 0.04),     # fused kernel, rows of <= 16 slots
+    (64, 128, 512, 2, 32, 0.4, 0.08),       # "halves" variant
+    (128, 256, 256, 2, 32, 0.5657, 0.16),   # one point per CTA
+    (1, 64, 1024, 2, 32, 0.2, 0.02),        # layer 0: occupancy features, one-channel route
+])
+def test_f16_forward_operands_vs_fp64_oracle(E, c_in, c_out, p_in, stride, nn_, radius, sigma):
+    """ops.forward_operands('f16') (epn_set_forward_operands): the no_grad forwards of the inter conv, the intra conv
+    and the 1x1 channel GEMM on fp16 hi/lo operands against the fp64 oracle port -- several times closer than the
+    default bf16 hi/lo operands on unit-scale inputs, and a training forward (kept tiles) is not affected."""
+    from oracle import torch_port as TP
+    torch.manual_seed(1)
+    conv = E.InterSO3Conv(c_in, c_out, 1, stride, radius, sigma, nn_, lazy_sample=True, kanchor=60).to(DEV)
+    xyz = sphere(1, p_in, 100 + p_in + c_in)
+    feats = torch.randn(1, c_in, p_in, 60, generator=torch.Generator().manual_seed(7)) if c_in > 1 else torch.ones(1, 1, p_in, 60)
+    W = conv.basic_conv.W.detach().cpu().double()
+    # indices from the fp32 coordinates (as on the GPU), kernel weights / features / GEMM in fp64
+    ry = TP.inter_so3conv(xyz, feats.double(), W, conv.anchors.cpu(), conv.kernels.cpu(), stride, nn_, radius, sigma,
+                          lazy_sample=True)[4]
+    x = E.SphericalPointCloud(xyz.to(DEV), feats.to(DEV), None)
+    err = {}
+    with torch.no_grad():
+        for fmt in ("bf16", "f16"):
+            with E.ops.forward_operands(fmt):
+                err[fmt] = rel_err(conv(x)[3].feats, ry)
+    print("inter %d->%d K=%d: bf16x3 %.2e, f16x3 %.2e" % (c_in, c_out, nn_, err["bf16"], err["f16"]))
+    assert err["f16"] < 1.5e-5 and err["bf16"] < FEAT_TOL and err["f16"] < err["bf16"]
+    with E.ops.forward_operands("f16"):     # under autograd the forward keeps bf16 tiles: bit-identical to the default
+        fg = feats.to(DEV).requires_grad_(True)
+        y_t = conv(E.SphericalPointCloud(xyz.to(DEV), fg, None))[3].feats
+    y_d = conv(E.SphericalPointCloud(xyz.to(DEV), feats.to(DEV).requires_grad_(True), None))[3].feats
+    assert torch.equal(y_t, y_d)
+    # intra conv + 1x1 channel GEMM on the (unit-scale) output
+    zin = torch.nn.functional.leaky_relu(torch.nn.functional.instance_norm(ry.float()))
+    intra = E.IntraSO3Conv(c_out, c_out).to(DEV)
+    rz = TP.intra_so3conv(zin.double(), intra.basic_conv.W.detach().cpu().double(), intra.intra_idx.cpu())
+    w1 = torch.randn(c_out, c_out, generator=torch.Generator().manual_seed(3)) / c_out ** 0.5
+    r1 = torch.einsum("oc,bcpa->bopa", w1.double(), zin.double())
+    with torch.no_grad():
+        for fmt in ("bf16", "f16"):
+            with E.ops.forward_operands(fmt):
+                err[fmt] = rel_err(intra(E.SphericalPointCloud(None, zin.to(DEV), None)).feats, rz)
+                err[fmt + "_1x1"] = rel_err(E.ops.basic_conv_fwd(zin.to(DEV).unsqueeze(2), w1.to(DEV)), r1)
+    print("intra %d: bf16x3 %.2e, f16x3 %.2e;  1x1: bf16x3 %.2e, f16x3 %.2e" % (c_out, err["bf16"], err["f16"], err["bf16_1x1"], err["f16_1x1"]))
+    assert err["f16"] < 1.5e-5 and err["f16"] < 0.6 * err["bf16"]
+    assert err["f16_1x1"] < 1.5e-5 and err["f16_1x1"] < 0.6 * err["bf16_1x1"]
+
+
+def test_f16_forward_operands_overflow_is_loud(E):
+    """Activations beyond fp16's range do not give silently wrong numbers under 'f16': the output is non-finite;
+    the default bf16 operands handle the same input."""
+    w = torch.randn(32, 32, device=DEV) / 32 ** 0.5
+    x = torch.randn(2, 32, 1, 64, 60, device=DEV) * 1e6
+    with torch.no_grad():
+        ref = torch.einsum("oc,bckpa->bopa", w.double(), x.double())
+        assert rel_err(E.ops.basic_conv_fwd(x, w), ref) < FEAT_TOL
+        with E.ops.forward_operands("f16"):
+            assert not bool(torch.isfinite(E.ops.basic_conv_fwd(x, w)).all())
+
+
 # ------------------------------------------------------------ whole network vs the reference's own GPU path
 def test_cls_network_b32_vs_reference_modules_on_gpu(E):
     """BASELINE configs[1] batch (32 clouds): head features and logits of this engine against the REFERENCE's own
@@ -233,15 +294,22 @@ def test_cls_network_b32_vs_reference_modules_on_gpu(E):
     e_feat, e_logit = rel_err(fo, fr), rel_err(lo, lr)
     rms = float((fo - fr).double().square().mean().sqrt() / fr.double().square().mean().sqrt())
     print("cls network B=32: head feature max-rel err %.2e (rms-rel %.2e), logits max-rel err %.2e" % (e_feat, rms, e_logit))
-    # Two independently rounded fp32 evaluations of 14 chained conv layers + 21 normalisations.  Every LAYER of this
-    # engine holds the 1e-4 bar against the oracle at full size (test_cls_layers_full_size_vs_oracle_port, features
-    # and gradients).  Chained, the bf16 hi/lo operands of the tensor-core GEMMs (x = hi + lo + e, |e| <= 2^-18 |x|)
-    # accumulate: measured 1.5e-4 rms-relative / 1.6e-4 max-relative on the 31 M head features of the 32-cloud batch
-    # (the reference's own fp32 chain sits ~1e-5 from fp64).  The whole-network figure therefore
-    # MISSES north_star's 1e-4 by 1.6x and the bar below says so: it is the measured value with 25 % headroom.
-    # What would close it -- an fp16 lo part (3 more mantissa bits) -- needs MMAs with a bf16 and an fp16 operand,
-    # which tcgen05.mma kind::f16 rejects on this GPU (illegal instruction, measured); see DESIGN.md section 2.
-    assert rms < 2e-4 and e_feat < 2e-4 and e_logit < 2e-4, (rms, e_feat, e_logit)
+    # Two independently rounded fp32 evaluations of 14 chained conv layers + 21 normalisations (the reference's own fp32
+    # chain sits ~1e-5 from fp64).  The no_grad forward of the block wrappers runs its GEMMs on
+    # fp16 hi/lo operands (blocks.fwd_operands): north_star's 1e-4 bar holds for the whole network.
+    assert rms < 1e-4 and e_feat < 1e-4 and e_logit < 1e-4, (rms, e_feat, e_logit)
+    # the same forward on the default bf16 hi/lo operands (what a training forward uses): measured 1.5e-4 rms-relative,
+    # i.e. 1.6x over the bar -- stated, with 25 % headroom
+    from epn_pointcloud_b200 import blocks
+    blocks.set_inference_operands("bf16")
+    try:
+        with torch.no_grad():
+            lo2, fo2 = ours(x)
+    finally:
+        blocks.set_inference_operands("f16")
+    rms2 = float((fo2 - fr).double().square().mean().sqrt() / fr.double().square().mean().sqrt())
+    print("  same network on bf16 hi/lo operands: head feature max-rel err %.2e (rms-rel %.2e)" % (rel_err(fo2, fr), rms2))
+    assert rms2 < 2e-4 and rel_err(fo2, fr) < 2e-4 and rms < 0.7 * rms2
 
 
 # ------------------------------------------------------------ f3 on the device
