@@ -325,6 +325,78 @@ def test_backbone_small_vs_golden(E):
         assert e_ref < 1e-3 and e_mine < 3e-2, (k, e_mine, e_ref)
 
 
+def test_backbone_small_chained_gradients_with_matched_kinks(E, monkeypatch):
+    """The chained-gradient comparison above is dominated by leaky_relu kink decisions (a pre-activation within rounding
+    distance of 0 takes slope 1 in one evaluation and 0.01 in the other; one flipped element of a 61 k-element map is a
+    4e-3 relative change of every gradient upstream of it).  Here the fp64 reference is evaluated WITH THE ENGINE'S OWN
+    kink decisions -- the sign pattern of each of the engine's 9 activations is recorded and imposed on the fp64
+    chain -- so what remains is the arithmetic of the backward kernels (norm backward, dX / dW GEMMs, scatter, intra
+    reduction) chained over three blocks: held to 1e-4 relative Frobenius, tensor by tensor (measured 1.2e-5 .. 1.7e-5)."""
+    import torch.nn.functional as F
+    from epn_pointcloud_b200 import blocks
+    from epn_pointcloud_b200.blocks import SO3ConvBackbone
+    from oracle import torch_port as TP
+    g = load_golden("backbone_small")
+    model = SO3ConvBackbone(g["params"], 60).to(DEV).train()
+    model.load_state_dict(g.state_dict(), strict=True)
+    masks = []
+    orig = blocks._norm_act
+
+    def recording(norm, x, act, residual=None, bias=None):
+        y = orig(norm, x, act, None, bias)          # the residual is added outside so that the sign is visible
+        masks.append((y.detach() > 0).cpu())
+        return y if residual is None else y + residual
+
+    monkeypatch.setattr(blocks, "_norm_act", recording)
+    y = model(g["pc"].to(DEV))
+    (y.feats * g["r"].to(DEV)).sum().backward()
+    monkeypatch.setattr(blocks, "_norm_act", orig)
+    assert len(masks) == 9
+
+    layers = TP.layers_from_module(model)
+    leaves, it = {}, iter(masks)
+
+    def lrelu(z):   # leaky_relu with the engine's decision: same value wherever the two agree on the sign
+        m = next(it)
+        return torch.where(m, z, 0.01 * z)
+
+    pc = g["pc"]
+    xyz = pc.permute(0, 2, 1).contiguous()
+    feats = torch.ones(pc.shape[0], 1, pc.shape[1], 60, dtype=torch.float64)
+    for li, (prm, args, intra_idx, anchors, kernels) in enumerate(layers):
+        prm = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+        for k, v in prm.items():
+            leaves[(li, k)] = v
+        norm = args.get("norm")
+        skip = feats
+        _, _, sidx, nxyz, x = TP.inter_so3conv(xyz, feats, prm["inter_W"], anchors, kernels, args["stride"], args["n_neighbor"],
+                                               args["radius"], args["sigma"], args["lazy_sample"])
+        x = lrelu(TP._norm(x, norm, prm.get("inter_bn_w"), prm.get("inter_bn_b")))
+        x = lrelu(TP._norm(TP.intra_so3conv(x, prm["intra_W"], intra_idx), None))
+        if args["stride"] > 1:
+            b, c, _, a = skip.shape
+            skip = torch.gather(skip, 2, sidx.long().view(b, 1, -1, 1).expand(b, c, sidx.shape[1], a))
+        skip = lrelu(TP._norm(F.conv2d(skip, prm["skip_w"], prm["skip_b"]), norm, prm.get("bn_w"), prm.get("bn_b")))
+        xyz, feats = nxyz, x + skip
+    assert rel_err(y.feats, feats) < FEAT_TOL
+    (feats * g["r"].double()).sum().backward()
+    names = {"backbone.0.blocks.0.inter_conv.conv.basic_conv.W": (0, "inter_W"),
+             "backbone.0.blocks.0.intra_conv.conv.basic_conv.W": (0, "intra_W"),
+             # (block 0's skip conv sees the constant occupancy features: its BatchNorm output is beta and its weight
+             #  gradient exactly zero -- nothing to compare)
+             "backbone.0.blocks.1.inter_conv.conv.basic_conv.W": (1, "inter_W"),
+             "backbone.0.blocks.1.intra_conv.conv.basic_conv.W": (1, "intra_W"),
+             "backbone.0.blocks.1.skip_conv.weight": (1, "skip_w"),
+             "backbone.1.blocks.0.inter_conv.conv.basic_conv.W": (2, "inter_W"),
+             "backbone.1.blocks.0.intra_conv.conv.basic_conv.W": (2, "intra_W")}
+    params = dict(model.named_parameters())
+    for k, key in names.items():
+        truth = leaves[key].grad.reshape(params[k].shape)
+        e = float((params[k].grad.double().cpu() - truth).norm() / truth.norm())
+        print("chained grad, matched kinks %s: %.2e" % (k, e))
+        assert e < FEAT_TOL, (k, e)
+
+
 # ------------------------------------- BASELINE-size cases: oracle-free properties
 def _layer(E, c_in, c_out, stride, nn_, radius, sigma, lazy=True):
     torch.manual_seed(0)
@@ -813,7 +885,7 @@ def test_inv_model_vs_reference_golden(E):
         desc, attn = model(g["pc"].to(DEV))
     assert desc.shape == g["desc"].shape and attn.shape == g["attn"].shape
     print("inv model golden: desc %.2e attn %.2e" % (rel_err(desc, g["desc"]), rel_err(attn, g["attn"])))
-    assert rel_err(desc, g["desc"]) < 2e-4 and rel_err(attn, g["attn"]) < 2e-4
+    assert rel_err(desc, g["desc"]) < FEAT_TOL and rel_err(attn, g["attn"]) < FEAT_TOL   # measured 5e-6
 
 
 def test_reg_model_vs_reference_golden(E):
@@ -827,7 +899,7 @@ def test_reg_model_vs_reference_golden(E):
         conf, quats = model(g["pairs"].to(DEV))
     assert conf.shape == g["conf"].shape and quats.shape == g["quats"].shape
     print("reg model golden: conf %.2e quats %.2e" % (rel_err(conf, g["conf"]), rel_err(quats, g["quats"])))
-    assert rel_err(conf, g["conf"]) < 2e-4 and rel_err(quats, g["quats"]) < 2e-4
+    assert rel_err(conf, g["conf"]) < FEAT_TOL and rel_err(quats, g["quats"]) < FEAT_TOL   # measured 7e-6 / 1.2e-5
 
 
 @pytest.mark.parametrize("which", ["inv", "reg"])

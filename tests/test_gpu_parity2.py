@@ -294,12 +294,15 @@ def test_cls_network_b32_vs_reference_modules_on_gpu(E):
     e_feat, e_logit = rel_err(fo, fr), rel_err(lo, lr)
     rms = float((fo - fr).double().square().mean().sqrt() / fr.double().square().mean().sqrt())
     print("cls network B=32: head feature max-rel err %.2e (rms-rel %.2e), logits max-rel err %.2e" % (e_feat, rms, e_logit))
-    # Two independently rounded fp32 evaluations of 14 chained conv layers + 21 normalisations (the reference's own fp32
-    # chain sits ~1e-5 from fp64).  The no_grad forward of the block wrappers runs its GEMMs on
-    # fp16 hi/lo operands (blocks.fwd_operands): north_star's 1e-4 bar holds for the whole network.
+    # Two independently rounded fp32 evaluations of 14 chained conv layers + 21 normalisations; measured 3.5e-5 max-rel /
+    # 3.1e-5 rms-rel on the 31 M head features (the reference's own fp32 chain sits ~1e-5 from fp64 at the last block,
+    # this engine 6e-6: tools/diag_chain_precision.py).  What it took: fp64 statistics and a
+    # subtract-first apply in the norm kernels (block 0 normalises a CONSTANT tensor -- the skip conv of the all-ones
+    # occupancy features -- where one ulp of the mean becomes 1e-5 of the output), a separate TMEM accumulator for the
+    # hi*lo cross products (the tensor core truncates the accumulator after every MMA), and fp16 hi/lo operands for
+    # the no_grad forward of the block wrappers (blocks.fwd_operands).
     assert rms < 1e-4 and e_feat < 1e-4 and e_logit < 1e-4, (rms, e_feat, e_logit)
-    # the same forward on the default bf16 hi/lo operands (what a training forward uses): measured 1.5e-4 rms-relative,
-    # i.e. 1.6x over the bar -- stated, with 25 % headroom
+    # the same forward on the default bf16 hi/lo operands (what a training forward uses): measured 5.5e-5 / 4.9e-5
     from epn_pointcloud_b200 import blocks
     blocks.set_inference_operands("bf16")
     try:
@@ -309,7 +312,7 @@ def test_cls_network_b32_vs_reference_modules_on_gpu(E):
         blocks.set_inference_operands("f16")
     rms2 = float((fo2 - fr).double().square().mean().sqrt() / fr.double().square().mean().sqrt())
     print("  same network on bf16 hi/lo operands: head feature max-rel err %.2e (rms-rel %.2e)" % (rel_err(fo2, fr), rms2))
-    assert rms2 < 2e-4 and rel_err(fo2, fr) < 2e-4 and rms < 0.7 * rms2
+    assert rms2 < 1e-4 and rel_err(fo2, fr) < 1e-4 and rms < rms2
 
 
 # ------------------------------------------------------------ f3 on the device
