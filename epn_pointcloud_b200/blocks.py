@@ -68,6 +68,90 @@ def fwd_operands(feats=None, occupancy=False):
     return ops.forward_operands("f16" if ok else "bf16")
 
 
+def _bn_track(norm, stats, count, bias=None):
+    """The running-statistics bookkeeping of nn.BatchNorm2d.forward in training mode, from the batch (mean, rstd) the
+    fused kernels computed; `bias`: a per-channel constant that was left out of the kernel's input (see norm_act)."""
+    if not norm.track_running_stats:
+        return
+    with torch.no_grad():
+        norm.num_batches_tracked += 1
+        mean = stats[0] if bias is None else stats[0] + bias.detach()
+        var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))
+        if norm.momentum is not None:
+            m = norm.momentum
+            norm.running_mean.mul_(1 - m).add_(mean, alpha=m)
+            norm.running_var.mul_(1 - m).add_(var, alpha=m)
+        else:  # cumulative moving average: the factor stays on the device (no host sync, graph-capturable)
+            m = 1.0 / norm.num_batches_tracked.to(torch.float32)
+            norm.running_mean.add_((mean - norm.running_mean) * m)
+            norm.running_var.add_((var - norm.running_var) * m)
+
+
+class _NormIntraFn(torch.autograd.Function):
+    """IntraSO3Conv(leaky_relu(norm(x))) with the normalised activation never written to memory: the statistics come
+    from one pass over x, the normalisation + activation are applied while the intra conv builds its operand tiles
+    (ops.intra_so3conv_fwd_norm; SURVEY 8 row f1, base_so3conv.py:116-126 -> :52-62).  Backward: intra conv backward
+    from the kept tiles (dW) and the permuted GEMM (gradient of the activation), then the norm backward from x and
+    the statistics -- neither needs the activation.  Falls back to the two separate ops (keeping the activation for
+    the backward's re-gather) when the shape is not covered or no memory is granted for the kept tiles."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, W, intra_idx, mode, eps, slope, given_stats, training):
+        x, W = x.contiguous(), W.contiguous()
+        kmode = 1 if mode == 2 else mode
+        stats = given_stats if mode == 2 else ops.norm_stats(x, mode, eps)
+        keep = bool(training) and bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[3])
+        res = ops.intra_so3conv_fwd_norm(x, stats, gamma, beta, kmode, slope, intra_idx, W, keep_grouped=keep)
+        y = None
+        if res is None:
+            y = ops.norm_act_fwd(x, gamma, beta, mode, eps, slope, stats=stats if mode == 2 else None)[0]
+            res = ops.intra_so3conv_fwd(y, intra_idx, W, keep_grouped=keep)
+        out, ctx.grouped = res if keep else (res, None)
+        ctx.save_for_backward(x, stats, gamma, beta, W, intra_idx, *([y] if (y is not None and ctx.grouped is None) else []))
+        ctx.mode, ctx.slope = kmode, slope
+        ctx.mark_non_differentiable(stats)
+        return out, stats
+
+    @staticmethod
+    def backward(ctx, dout, _dstats):
+        saved = list(ctx.saved_tensors)
+        x, stats, gamma, beta, W, intra_idx = saved[:6]
+        y = saved[6] if len(saved) > 6 else x       # only read when there are no kept tiles
+        dy, dW = ops.intra_so3conv_bwd(dout.contiguous(), y, intra_idx, W, True, ctx.needs_input_grad[3], grouped=ctx.grouped)
+        ctx.grouped = None
+        dx, dgamma, dbeta = ops.norm_act_bwd(dy, x, gamma, beta, stats, ctx.mode, ctx.slope)
+        return dx, dgamma, dbeta, dW, None, None, None, None, None, None
+
+
+def norm_intra(norm, x, act, intra):
+    """`intra(act(norm(x)))` for x = the raw output of a conv and `intra` an IntraSO3Conv module, as one fused op when
+    (norm, act) is one of the combinations norm_act fuses; returns None when it is not (caller runs the two ops)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and act is F.leaky_relu and x.dim() == 4 and _FUSE_NORM_INTRA):
+        return None
+    if torch.is_grad_enabled() and not _FUSE_NORM_INTRA_TRAINING:
+        return None
+    W, idx = intra.basic_conv.W, intra._intra_idx32
+    if isinstance(norm, nn.InstanceNorm2d) and not norm.affine and not norm.track_running_stats:
+        return _NormIntraFn.apply(x, None, None, W, idx, 0, norm.eps, 0.01, None, torch.is_grad_enabled())[0]
+    if isinstance(norm, nn.BatchNorm2d) and norm.training and norm.affine:
+        out, stats = _NormIntraFn.apply(x, norm.weight, norm.bias, W, idx, 1, norm.eps, 0.01, None, torch.is_grad_enabled())
+        _bn_track(norm, stats, x.numel() // x.shape[1])
+        return out
+    if (isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats and norm.running_mean is not None
+            and not torch.is_grad_enabled()):
+        stats = torch.stack((norm.running_mean, torch.rsqrt(norm.running_var + norm.eps))).contiguous()
+        return _NormIntraFn.apply(x, norm.weight, norm.bias, W, idx, 2, norm.eps, 0.01, stats, False)[0]
+    return None
+
+
+_FUSE_NORM_INTRA = True   # tests switch it off to compare the fused pair with the two separate ops
+# Under autograd the fused pair is correct (tested) but NOT faster on the B200: the training forward builds the kept
+# operand tiles with a 12x gather (intra_tiles_rows_kernel, HBM-write-bound), and normalising every gathered element
+# there doubles that kernel's instruction count (measured 3.95 -> 8.0 ms per step against 0.5 ms saved in the norm
+# kernels).  So by default only no_grad forwards fuse (29.35 -> 28.9 ms inference forward).
+_FUSE_NORM_INTRA_TRAINING = False
+
+
 def norm_act(norm, x, act, residual=None, bias=None):
     return _mark_unit(_norm_act(norm, x, act, residual, bias))
 
@@ -87,20 +171,7 @@ def _norm_act(norm, x, act, residual=None, bias=None):
         return _NormActFn.apply(x, None, None, 0, norm.eps, slope, residual, bias)[0]
     if fusable and isinstance(norm, nn.BatchNorm2d) and norm.training and norm.affine:
         y, stats = _NormActFn.apply(x, norm.weight, norm.bias, 1, norm.eps, slope, residual, bias)
-        if norm.track_running_stats:  # same bookkeeping as nn.BatchNorm2d.forward
-            with torch.no_grad():
-                count = x.numel() // x.shape[1]
-                norm.num_batches_tracked += 1
-                mean = stats[0] if bias is None else stats[0] + bias.detach()
-                var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))
-                if norm.momentum is not None:
-                    m = norm.momentum
-                    norm.running_mean.mul_(1 - m).add_(mean, alpha=m)
-                    norm.running_var.mul_(1 - m).add_(var, alpha=m)
-                else:  # cumulative moving average: the factor stays on the device (no host sync, graph-capturable)
-                    m = 1.0 / norm.num_batches_tracked.to(torch.float32)
-                    norm.running_mean.add_((mean - norm.running_mean) * m)
-                    norm.running_var.add_((var - norm.running_var) * m)
+        _bn_track(norm, stats, x.numel() // x.shape[1], bias)
         return y
     if (fusable and isinstance(norm, nn.BatchNorm2d) and not norm.training and norm.track_running_stats
             and norm.running_mean is not None and not (torch.is_grad_enabled() and x.requires_grad)):
@@ -199,9 +270,24 @@ class SeparableSO3ConvBlock(nn.Module):
     def forward(self, x, inter_idx, inter_w):
         skip_feature = x.feats
         skip_unit = bool(getattr(x, "is_occupancy", False)) or getattr(skip_feature, "_epn_unit", False)
-        inter_idx, inter_w, sample_idx, x = self.inter_conv(x, inter_idx, inter_w)
-        if self.use_intra:
-            x = self.intra_conv(x)
+        fused = None
+        ic, ia = self.inter_conv, (self.intra_conv if self.use_intra else None)
+        if ia is not None and not (self.training and (ic.dropout is not None or ia.dropout is not None)):
+            # inter conv -> [norm + act applied inside the intra conv's operand load] -> intra conv -> norm + act
+            occ = bool(getattr(x, "is_occupancy", False))
+            with fwd_operands(None if occ else x.feats, occupancy=occ):
+                inter_idx, inter_w, sample_idx, xr = ic.conv(x, inter_idx, inter_w)
+            with fwd_operands(occupancy=True):   # the intra conv's operand is a normalised activation by construction
+                fused = norm_intra(ic.norm, xr.feats, ic.relu, ia.conv)
+            if fused is not None:
+                x = sptk.SphericalPointCloud(xr.xyz, norm_act(ia.norm, fused, ia.relu), ia.conv.anchors)
+            else:      # not a fusable combination: finish the inter block the ordinary way
+                xr = sptk.SphericalPointCloud(xr.xyz, norm_act(ic.norm, xr.feats, ic.relu), xr.anchors)
+                x = ia(xr)
+        else:
+            inter_idx, inter_w, sample_idx, x = self.inter_conv(x, inter_idx, inter_w)
+            if self.use_intra:
+                x = self.intra_conv(x)
         if self.stride > 1:
             if self.inter_conv.conv.lazy_sample:   # prefix sampling (pc/sample.py:64-67): the gather is a slice
                 skip_feature = skip_feature[:, :, :sample_idx.shape[1]]

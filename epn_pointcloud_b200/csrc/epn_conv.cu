@@ -572,10 +572,13 @@ EPN_API size_t epn_intra_so3conv_grouped_bytes(int b, int c_in, int p, int na, i
     return grouped_tiles_bytes(b, c_in * kn, p, na);
 }
 
-EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
-                                      void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
-                                      unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
-                                      int kn, void *stream) {
+// pro != NULL: feats is the RAW output of the preceding conv and the normalisation + leaky_relu that follows it is applied
+// while the operand tiles are built (tile routes only: anything else returns EPN_ERR_SHAPE and the caller runs the
+// norm kernel itself)
+static int intra_fwd_impl(const float *feats, const int32_t *intra_idx, const float *W, float *out,
+                          void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                          unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
+                          int kn, void *stream, const NormPrologue *pro) {
     EPN_REQUIRE_PTR(feats); EPN_REQUIRE_PTR(intra_idx); EPN_REQUIRE_PTR(W); EPN_REQUIRE_PTR(out);
     EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c_in); EPN_REQUIRE_POS(c_out); EPN_REQUIRE_POS(p); EPN_REQUIRE_POS(na);
     EPN_REQUIRE_POS(kn); EPN_CHECK_B(b);
@@ -602,9 +605,14 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
                 // inference (no operand tiles to keep for the weight gradient): Y_k = W_k . feats on the tensor cores,
                 // out = sum_k Y_k permuted, reduced in shared memory -- the 12x larger grouped tensor never exists
                 const float *fz = feats + (size_t)b0 * c_in * p * na;
+                NormPrologue pz;
+                if (pro != nullptr) {
+                    pz = *pro;
+                    if (pz.mode == 0) pz.stats += (size_t)b0 * c_in;   // instance statistics of the slab's first cloud
+                }
                 const int rc = launch_umma_intra_dx(fz, (long long)c_in * p * na, (long long)p * na, W, intra_idx,
                                                     out + (size_t)b0 * c_out * p * na, ws.slab, ws.tilesA, bc, c_in, c_out, p, 1, s,
-                                                    fwd_fmt());
+                                                    fwd_fmt(), pro ? &pz : nullptr);
                 if (rc == 0) continue;
                 if (rc != 1) return rc;
             }
@@ -612,10 +620,16 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
             if (keep) keep += split_tiles_bytes(n_slab, ck, 128);
             int direct = 1;
             if (gemm_backend() == 0) {
+                NormPrologue pz;
+                if (pro != nullptr) {
+                    pz = *pro;
+                    if (pz.mode == 0) pz.stats += (size_t)b0 * c_in;
+                }
                 direct = launch_intra_group_tiles(feats + (size_t)b0 * c_in * p * na, intra_idx, tiles, 0, p0, pc, bc, c_in,
-                                                  p, na, kn, s);
+                                                  p, na, kn, s, pro ? &pz : nullptr);
                 if (direct != 0 && direct != 1) return direct;
             }
+            EPN_REQUIRE(direct == 0 || pro == nullptr, EPN_ERR_SHAPE, "fused norm prologue: shape not covered by the tile routes");
             EPN_REQUIRE(direct == 0 || grouped == nullptr, EPN_ERR_SHAPE, "grouped tiles requested for an unsupported shape");
             if (direct == 0) {
                 EPN_TRY(gemm_fwd_tiles(tiles, c_out, ck, bc, cols, o, ws, s));
@@ -628,6 +642,34 @@ EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_i
         }
     }
     return 0;
+}
+
+EPN_API int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, const float *W, float *out,
+                                      void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                                      unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
+                                      int kn, void *stream) {
+    return intra_fwd_impl(feats, intra_idx, W, out, workspace, workspace_bytes, grouped, grouped_bytes, grouped_layout, b,
+                          c_in, c_out, p, na, kn, stream, nullptr);
+}
+
+EPN_API int epn_intra_so3conv_fwd_norm_f32(const float *x, const float *stats, const float *gamma, const float *beta,
+                                           int norm_mode, float slope, const int32_t *intra_idx, const float *W,
+                                           float *out, void *workspace, size_t workspace_bytes, void *grouped,
+                                           size_t grouped_bytes, unsigned long long *grouped_layout, int b, int c_in,
+                                           int c_out, int p, int na, int kn, void *stream) {
+    EPN_REQUIRE_PTR(stats);
+    EPN_REQUIRE(norm_mode == 0 || norm_mode == 1, EPN_ERR_SHAPE, "norm_mode must be 0 (instance) or 1 (batch)");
+    EPN_REQUIRE(gemm_backend() == 0, EPN_ERR_SHAPE, "fused norm prologue needs the tensor-core engine");
+    NormPrologue pro;
+    pro.stats = stats;
+    pro.gamma = gamma;
+    pro.beta = beta;
+    pro.mode = norm_mode;
+    pro.G = norm_mode == 0 ? b * c_in : c_in;
+    pro.c = c_in;
+    pro.slope = slope;
+    return intra_fwd_impl(x, intra_idx, W, out, workspace, workspace_bytes, grouped, grouped_bytes, grouped_layout, b, c_in,
+                          c_out, p, na, kn, stream, &pro);
 }
 
 EPN_API int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,

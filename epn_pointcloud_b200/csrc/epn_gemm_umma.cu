@@ -46,6 +46,12 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
                 if (kcg * 8 + i < K) x[i] = __ldg(base + kz * src.stride_kz + kj * src.stride_k);
                 if (++kj == src.k_per_z) { kj = 0; ++kz; }
             }
+            if (src.pro.stats != nullptr) {   // normalisation + leaky_relu of the producer, applied on the way in
+                const int z = (int)(row / src.rows_per_z);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (kcg * 8 + i < K) x[i] = src.pro.apply(x[i], z, kcg * 8 + i);
+            }
         }
         uint4 hi, lo;
         split8_fmt(x, hi, lo, fmt, scale);
@@ -107,7 +113,7 @@ int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long
     const int row_tiles = (int)((rows + tr - 1) / tr), k_blocks = (int)((K + KB - 1) / KB);
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     ProfScope prof(s, KC_SPLIT);
-    if (src.stride_k == 1 && src.stride_row != 1 && (rows_pad + 31) / 32 <= 65535) {
+    if (src.pro.stats == nullptr && src.stride_k == 1 && src.stride_row != 1 && (rows_pad + 31) / 32 <= 65535) {
         dim3 grid((kcgs + 7) / 8, (rows_pad + 31) / 32);
         split_tiles_kcontig_kernel<<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, k_blocks, fmt,
                                                         scale);
@@ -715,7 +721,7 @@ bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn) { return na == 6
 // grouped tensor (G resp. dG) only ever exists as one TMEM accumulator tile per SM.
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, int forward, cudaStream_t s, int fmt) {
+                         int c_out, int p, int forward, cudaStream_t s, int fmt, const NormPrologue *pro) {
     const long long n = (long long)bc * p * 60;
     if (!intra_dx_fused_ok(n, p, 60, 12) || n >= (1LL << 31)) return 1;
     const int c_rows = forward ? c_out : c_in, c_k = forward ? c_in : c_out;
@@ -730,6 +736,7 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
         if (rc) return rc;
     }
     SplitSrc src{dout, (long long)p * 60, dout_stride_z, 1, 1LL << 60, 0, dout_stride_o};
+    if (pro != nullptr) src.pro = *pro;
     int rc = launch_split_tiles(src, dout_tiles, n, c_k, 240, s, fmt);
     if (rc) return rc;
     static DynSmemOnce once3;

@@ -24,7 +24,7 @@ template <int NA, int KN, int PAIRS>
 __global__ void __launch_bounds__(256)
 intra_tiles_rows_kernel(const float *__restrict__ feats, const int32_t *__restrict__ intra_idx,
                         uint8_t *__restrict__ tiles, int k_blocks, int c, int p, int p_off, int p_cnt, int n_slab,
-                        int rows_pad) {
+                        int rows_pad, NormPrologue pro) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= rows_pad) return;
     const int cols = p_cnt * NA, kcgs = k_blocks * (KB / 8);
@@ -44,6 +44,13 @@ intra_tiles_rows_kernel(const float *__restrict__ feats, const int32_t *__restri
         for (int k = 0; k < KN; ++k) {
             v[k] = (row_ok && c0 < c) ? __ldg(frow0 + (size_t)c0 * cstride + ix[k]) : 0.f;
             v[KN + k] = (row_ok && c0 + 1 < c) ? __ldg(frow0 + (size_t)(c0 + 1) * cstride + ix[k]) : 0.f;
+        }
+        if (pro.stats != nullptr && row_ok) {   // the producer's normalisation + leaky_relu, applied on the way in
+#pragma unroll
+            for (int k = 0; k < KN; ++k) {
+                if (c0 < c) v[k] = pro.apply(v[k], z, c0);
+                if (c0 + 1 < c) v[KN + k] = pro.apply(v[KN + k], z, c0 + 1);
+            }
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
@@ -102,7 +109,7 @@ intra_tiles_cols_kernel(const float *__restrict__ feats, const int32_t *__restri
 bool intra_group_tiles_ok(int na, int kn) { return na == 60 && kn == 12; }
 
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
-                             int bc, int c, int p, int na, int kn, cudaStream_t s) {
+                             int bc, int c, int p, int na, int kn, cudaStream_t s, const NormPrologue *pro) {
     const long long n_slab = (long long)bc * p_cnt * na;
     const int ck = c * kn;
     if (n_slab >= (1LL << 31) - 4096 || !intra_group_tiles_ok(na, kn)) return 1;
@@ -116,8 +123,10 @@ int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void 
         dim3 grid((rows_pad + 255) / 256, (pairs + PAIRS - 1) / PAIRS);
         if (grid.y > 65535) return 1;
         intra_tiles_rows_kernel<60, 12, PAIRS><<<grid, 256, 0, s>>>(feats, intra_idx, static_cast<uint8_t *>(tiles), k_blocks,
-                                                                  c, p, p_off, p_cnt, (int)n_slab, rows_pad);
+                                                                  c, p, p_off, p_cnt, (int)n_slab, rows_pad,
+                                                                  pro ? *pro : NormPrologue());
     } else {
+        if (pro != nullptr) return 1;   // the column-major variant (backward re-gather) has no prologue
         constexpr int CPT = 8;
         dim3 grid((rows_pad + 255) / 256, (kcgs + CPT - 1) / CPT);
         if (grid.y > 65535) return 1;

@@ -12,6 +12,22 @@ struct InterGeom {
     float sigma;
 };
 
+// Normalisation + leaky_relu applied to a feature tensor [z, c, n] WHILE a consumer loads it (the
+// "next prologue" half of the norm fusion): y = lrelu((x - mean_g) * rstd_g * gamma_ch + beta_ch), stats[g] = mean,
+// stats[G + g] = rstd with g = z * c + ch (mode 0, InstanceNorm2d) or g = ch (mode 1, BatchNorm2d).  stats == NULL: off.
+struct NormPrologue {
+    const float *stats = nullptr;
+    const float *gamma = nullptr, *beta = nullptr;   // NULL = 1 / 0
+    int mode = 0, G = 0, c = 0;
+    float slope = 0.01f;
+    __device__ __forceinline__ float apply(float x, int z, int ch) const {
+        const int g = mode == 0 ? z * c + ch : ch;
+        const float mean = __ldg(stats + g), sc = __ldg(stats + G + g) * (gamma ? __ldg(gamma + ch) : 1.f);
+        const float v = fmaf(x - mean, sc, beta ? __ldg(beta + ch) : 0.f);
+        return v > 0.f ? v : v * slope;
+    }
+};
+
 // Kernel weight relu(1 - |g - r|^2 / sigma) in the reference's fp32 operation order
 // (so3conv/functional.py:198-200: square, (x+y)+z, true division, subtract; no FMA contraction), so the
 // weights agree with the reference to the last bit for identical rotated kernel points.
@@ -149,7 +165,7 @@ int launch_inter_group_occ(const float *feats, const int32_t *idx, const InterGe
 
 // epn_group_tiles2.cu -- return 1 if the shape is unsupported (caller falls back)
 int launch_intra_group_tiles(const float *feats, const int32_t *intra_idx, void *tiles, int mode, int p_off, int p_cnt,
-                             int bc, int c, int p, int na, int kn, cudaStream_t s);
+                             int bc, int c, int p, int na, int kn, cudaStream_t s, const NormPrologue *pro = nullptr);
 int launch_inter_scatter(const float *dG, long long stride_b, long long stride_ck, const int32_t *idx,
                          const InterGeom &g, float *dfeats, int p_off, int p_cnt, int bc, int c, int p_in, int p, int nn,
                          int na, int ks, cudaStream_t s);
@@ -162,6 +178,7 @@ struct SplitSrc {
     const float *ptr;
     long long rows_per_z, stride_rz, stride_row;
     long long k_per_z, stride_kz, stride_k;
+    NormPrologue pro;   // applied to element (row, k) with z = row / rows_per_z, ch = k (k_per_z must cover K)
 };
 // Where the GEMM writes D[row, col]: out + (row / rows_per_z) * stride_z + (row % rows_per_z) * stride_row
 //                                        + col * stride_col      (atomic: RED add instead of store)
@@ -189,7 +206,7 @@ size_t intra_dx_dout_bytes(long long n, int c_k);
 bool intra_dx_fused_ok(long long n_cols, int p, int na, int kn);
 int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long dout_stride_o, const float *W,
                          const int32_t *intra_idx, float *dfeats, void *wt_tiles, void *dout_tiles, int bc, int c_in,
-                         int c_out, int p, int forward, cudaStream_t s, int fmt = 0);
+                         int c_out, int p, int forward, cudaStream_t s, int fmt = 0, const NormPrologue *pro = nullptr);
 
 // epn_gemm_dw.cu -- dW[c_out, ck] += dout . G straight from the forward operand tiles of a slab
 // (rows = n grouped columns, n % 128 == 0, K = ck), read as the MN-major M operand; B_tiles = dout tiles

@@ -248,6 +248,27 @@ EPN_API int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float
     return check_launch("norm_apply_kernel");
 }
 
+// statistics only: what epn_norm_act_fwd_f32 computes before its apply pass (for consumers that apply the
+// normalisation themselves while loading, epn_intra_so3conv_fwd_norm_f32)
+EPN_API int epn_norm_stats_f32(const float *x, float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n,
+                               int mode, float eps, void *stream) {
+    EPN_REQUIRE_PTR(x); EPN_REQUIRE_PTR(stats); EPN_REQUIRE_PTR(workspace);
+    EPN_REQUIRE_POS(b); EPN_REQUIRE_POS(c); EPN_REQUIRE_POS(n);
+    EPN_REQUIRE(mode == 0 || mode == 1, EPN_ERR_SHAPE, "mode must be 0 (instance) or 1 (batch)");
+    EPN_REQUIRE((long long)b * c <= 2147483647LL / 2, EPN_ERR_SHAPE, "b*c too large");
+    EPN_REQUIRE(workspace_bytes >= epn_norm_act_workspace_bytes(b, c), EPN_ERR_WORKSPACE, "workspace too small");
+    EPN_REQUIRE(((uintptr_t)x & 15) == 0, EPN_ERR_ALIGN, "x must be 16-byte aligned");
+    cudaStream_t s = as_stream(stream);
+    double2 *part = static_cast<double2 *>(workspace);
+    const int rows = b * c, G = mode == 0 ? rows : c;
+    ProfScope prof(s, KC_NORM);
+    norm_row_stats_kernel<<<rows, NT, 0, s>>>(x, part, n);
+    int rc = check_launch("norm_row_stats_kernel");
+    if (rc) return rc;
+    norm_finalize_kernel<<<cdiv(G, 128), 128, 0, s>>>(part, stats, b, c, n, mode, eps);
+    return check_launch("norm_finalize_kernel");
+}
+
 EPN_API int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *gamma, const float *beta,
                                  const float *stats, float *dx, float *dgamma, float *dbeta, void *workspace,
                                  size_t workspace_bytes, int b, int c, int n, int mode, float slope, void *stream) {

@@ -416,6 +416,37 @@ def intra_so3conv_fwd(feats, intra_idx, W, keep_grouped=False):
     return (out, _Grouped.wrap(grouped, layout.value)) if keep_grouped else out
 
 
+def intra_so3conv_fwd_norm(x, stats, gamma, beta, mode, slope, intra_idx, W, keep_grouped=False):
+    """IntraSO3Conv applied to leaky_relu(norm(x) * gamma + beta, slope) WITHOUT materialising that activation: x
+    [b,c,p,na] is the raw output of the preceding conv, stats [2,G] its (mean, rstd) (norm_stats, or the running
+    statistics of an evaluation-mode BatchNorm with mode 1); the normalisation is applied while the operand tiles are
+    built (epn_intra_so3conv_fwd_norm_f32).  Returns None instead of raising when the shape is outside the tile
+    routes, so the caller can run the unfused sequence."""
+    _require_cuda(x, stats, gamma, beta, intra_idx, W)
+    b, c_in, p, na = x.shape
+    kn = intra_idx.shape[1]
+    c_out = W.shape[0]
+    if W.shape[1] != c_in * kn:
+        raise RuntimeError("W must be [c_out, c_in*kn]")
+    L = _lib.lib()
+    if L.epn_get_gemm_backend() != 0 or na != 60 or kn != 12 or p % 4 != 0:
+        return None
+    out = torch.empty(b, c_out, p, na, dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        wsb = L.epn_intra_so3conv_workspace_bytes(b, c_in, c_out, p, na, kn, 0)
+        ws = _workspace(wsb, x.device)
+        grouped = _grouped_buffer(L.epn_intra_so3conv_grouped_bytes(b, c_in, p, na, kn) if keep_grouped else 0,
+                                  x.device, keep_grouped)
+        if keep_grouped and grouped is None:
+            return None   # a backward without kept tiles would have to re-gather the (never materialised) activation
+        layout = ctypes.c_ulonglong(0)
+        _lib.check(L.epn_intra_so3conv_fwd_norm_f32(_p(x), _p(stats), _p(gamma), _p(beta), int(mode), float(slope), _p(intra_idx),
+                                                    _p(W), _p(out), _p(ws), wsb, _p(grouped),
+                                                    0 if grouped is None else grouped.numel(), ctypes.addressof(layout),
+                                                    b, c_in, c_out, p, na, kn, _stream()), "epn_intra_so3conv_fwd_norm_f32")
+    return (out, _Grouped.wrap(grouped, layout.value)) if keep_grouped else out
+
+
 def intra_so3conv_bwd(dout, feats, intra_idx, W, need_dfeats=True, need_dw=True, grouped=None):
     _require_cuda(dout, feats, intra_idx, W)
     b, c_in, p, na = feats.shape
@@ -455,6 +486,20 @@ def norm_act_fwd(x, gamma, beta, mode, eps, slope, residual=None, stats=None):
         _lib.check(L.epn_norm_act_fwd_f32(_p(x), _p(gamma), _p(beta), _p(residual), _p(y), _p(stats), _p(ws), wsb, b, c, n, int(mode),
                                           float(eps), float(slope), _stream()), "epn_norm_act_fwd_f32")
     return y, stats
+
+
+def norm_stats(x, mode, eps):
+    """(mean, rstd) [2,G] of x [b,c,p,a]: G = b*c (mode 0, InstanceNorm2d) or c (mode 1, BatchNorm2d batch statistics)."""
+    _require_cuda(x)
+    b, c = x.shape[0], x.shape[1]
+    n = x[0, 0].numel()
+    stats = torch.empty(2, b * c if mode == 0 else c, dtype=torch.float32, device=x.device)
+    L = _lib.lib()
+    with torch.cuda.device(x.device):
+        wsb = L.epn_norm_act_workspace_bytes(b, c)
+        ws = _workspace(wsb, x.device)
+        _lib.check(L.epn_norm_stats_f32(_p(x), _p(stats), _p(ws), wsb, b, c, n, int(mode), float(eps), _stream()), "epn_norm_stats_f32")
+    return stats
 
 
 def norm_act_bwd(dy, x, gamma, beta, stats, mode, slope, need_affine_grads=True):

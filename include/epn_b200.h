@@ -187,6 +187,16 @@ int epn_intra_so3conv_fwd_f32(const float *feats, const int32_t *intra_idx, cons
                               void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
                               unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
                               int kn, void *stream);
+/* IntraSO3ConvBlock fed by an Inter/IntraSO3ConvBlock WITHOUT materialising the normalised activation
+ * (SPConvNets/utils/base_so3conv.py:116-126 followed by :52-62): `x` [b,c_in,p,na] is the RAW output of the preceding
+ * convolution, `stats` its (mean, rstd) per group from epn_norm_stats_f32 (or, for an evaluation-mode BatchNorm, the
+ * running statistics), and feats = leaky_relu(norm(x) * gamma + beta, slope) is applied as the operand tiles are built.
+ * Everything else as epn_intra_so3conv_fwd_f32; shapes outside the tile routes return EPN_ERR_SHAPE. */
+int epn_intra_so3conv_fwd_norm_f32(const float *x, const float *stats, const float *gamma, const float *beta,
+                                   int norm_mode, float slope, const int32_t *intra_idx, const float *W, float *out,
+                                   void *workspace, size_t workspace_bytes, void *grouped, size_t grouped_bytes,
+                                   unsigned long long *grouped_layout, int b, int c_in, int c_out, int p, int na,
+                                   int kn, void *stream);
 /* feats may be NULL when grouped is given (dW then needs nothing else). */
 int epn_intra_so3conv_bwd_f32(const float *dout, const float *feats, const int32_t *intra_idx,
                               const float *W, float *dfeats, float *dW, void *workspace,
@@ -218,6 +228,9 @@ int epn_basic_conv_bwd_f32(const float *dout, const float *x, const float *W, fl
  * Backward writes dx fully and, for mode 1, dgamma/dbeta [c] (NULL to skip).
  * workspace: epn_norm_act_workspace_bytes(b, c) bytes. */
 size_t epn_norm_act_workspace_bytes(int b, int c);
+/* statistics only (mode 0 / 1; same workspace): for consumers that apply the normalisation while they load */
+int epn_norm_stats_f32(const float *x, float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n,
+                       int mode, float eps, void *stream);
 int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, const float *residual, float *y,
                          float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n, int mode,
                          float eps, float slope, void *stream);

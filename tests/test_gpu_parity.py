@@ -348,6 +348,7 @@ def test_backbone_small_chained_gradients_with_matched_kinks(E, monkeypatch):
         return y if residual is None else y + residual
 
     monkeypatch.setattr(blocks, "_norm_act", recording)
+    monkeypatch.setattr(blocks, "_FUSE_NORM_INTRA", False)   # every activation goes through norm_act
     y = model(g["pc"].to(DEV))
     (y.feats * g["r"].to(DEV)).sum().backward()
     monkeypatch.setattr(blocks, "_norm_act", orig)
@@ -838,6 +839,50 @@ def test_fused_norm_act_batchnorm_eval_mode(E):
     assert _lib.lib().epn_launch_count() - n0 == 1          # the apply kernel only
     assert rel_err(y, yr) < 1e-6
     assert torch.equal(mine.running_mean.cpu(), torch.linspace(-1, 1, c)) and int(mine.num_batches_tracked) == 0
+
+
+@pytest.mark.parametrize("norm_kind,mode", [("BatchNorm2d", "train"), ("BatchNorm2d", "eval"), (None, "train")])
+def test_norm_fused_into_intra_conv_equals_separate_ops(E, norm_kind, mode):
+    """SeparableSO3ConvBlock with the inter block's norm + leaky_relu applied inside the intra conv's operand load
+    (blocks.norm_intra, epn_intra_so3conv_fwd_norm_f32: the normalised activation is never written) against the same
+    block running the norm kernel and the intra conv separately: outputs, input / weight / affine gradients and the
+    BatchNorm running statistics; under no_grad (inference routes) and under autograd (kept tiles)."""
+    from epn_pointcloud_b200 import blocks
+    from epn_pointcloud_b200.blocks import SeparableSO3ConvBlock
+    args = dict(dim_in=16, dim_out=32, kernel_size=1, stride=1, radius=0.4, sigma=0.08, n_neighbor=16, multiplier=1,
+                kanchor=60, lazy_sample=True, norm=norm_kind, activation="leaky_relu", pooling="none", dropout_rate=0)
+    if norm_kind is None:
+        args.pop("norm")
+    torch.manual_seed(3)
+    blk = SeparableSO3ConvBlock(args).to(DEV)
+    blk.train(mode == "train")
+    xyz = sphere(3, 64, 5).to(DEV)
+    f0 = torch.randn(3, 16, 64, 60, device=DEV)
+    r = torch.randn(3, 32, 64, 60, device=DEV)
+    res = {}
+    state0 = {k: v.clone() for k, v in blk.state_dict().items()}
+    for fuse in (False, True):
+        blk.load_state_dict(state0)
+        blocks._FUSE_NORM_INTRA = fuse
+        blocks._FUSE_NORM_INTRA_TRAINING = fuse
+        try:
+            with torch.no_grad():
+                y_inf = blk(E.SphericalPointCloud(xyz, blocks._mark_unit(f0.clone()), None), None, None)[3].feats
+            out = [y_inf]
+            if mode == "train":
+                blk.load_state_dict(state0)
+                blk.zero_grad()
+                f = f0.clone().requires_grad_(True)
+                y = blk(E.SphericalPointCloud(xyz, f, None), None, None)[3].feats
+                (y * r).sum().backward()
+                out += [y.detach(), f.grad.clone()] + [p.grad.clone() for _, p in sorted(blk.named_parameters()) if p.grad is not None]
+                out += [v.clone().float() for k, v in sorted(blk.state_dict().items()) if "running" in k]
+            res[fuse] = out
+        finally:
+            blocks._FUSE_NORM_INTRA, blocks._FUSE_NORM_INTRA_TRAINING = True, False
+    assert len(res[True]) == len(res[False])
+    for a, b_ in zip(res[True], res[False]):
+        assert rel_err(a, b_) < 2e-5, (a.shape, rel_err(a, b_))
 
 
 # ------------------------------------------------------------ classification head + full model (8 f2)
