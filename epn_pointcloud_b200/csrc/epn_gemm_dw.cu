@@ -31,9 +31,15 @@ using namespace umma;
 
 namespace {
 
-constexpr int UNIT = 64;                          // n per pipeline stage
-constexpr uint32_t A_PART = 16 * UNIT * 16;       // 16 kk-groups x 64 n x 16 B
-constexpr uint32_t A_STAGE = 2 * A_PART;          // hi + lo = 32 KB
+// UNIT = n per pipeline stage: 64 (A stage 32 KB + two dout tiles), or 32 for C_out > 128 -- a 64-n stage of a
+// 256-row dout tile is 96 KB, i.e. ONE CTA per SM with two stages, which streamed at 3.1 TB/s (ncu launch list of the
+// step, the 21 launches of the C_out = 256 layers); 32-n stages are 48 KB: two CTAs per SM like the narrow layers.
+template <int UNIT> struct DwCfg {
+    static constexpr uint32_t A_PART = 16 * UNIT * 16;   // 16 kk-groups x UNIT n x 16 B
+    static constexpr uint32_t A_STAGE = 2 * A_PART;      // hi + lo
+    static constexpr int NB = UNIT / 32;                 // 32-n dout tiles per stage
+    static constexpr int UPT = 128 / UNIT;               // stages per 128-row forward tile
+};
 
 struct DwParams {
     const uint8_t *G;  // forward tiles [row_tiles][g_k_blocks]
@@ -44,8 +50,10 @@ struct DwParams {
     int ck, c_out, kperm;
 };
 
-template <bool TMA>
+template <bool TMA, int UNIT>
 __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_constant__ CUtensorMap g_map) {
+    constexpr uint32_t A_PART = DwCfg<UNIT>::A_PART, A_STAGE = DwCfg<UNIT>::A_STAGE;
+    constexpr int NB = DwCfg<UNIT>::NB, UPT = DwCfg<UNIT>::UPT;
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per = (p.units + p.split_k - 1) / p.split_k;
@@ -54,7 +62,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_c
     if (nu <= 0) return;  // uniform for the CTA
 
     const uint32_t b_tile = (uint32_t)tile_bytes(p.trb);
-    const uint32_t stage_bytes = A_STAGE + 2 * b_tile;
+    const uint32_t stage_bytes = A_STAGE + NB * b_tile;
     const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t bars = base + p.stages * stage_bytes;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -90,7 +98,7 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_c
         const int kb = 4 * blockIdx.x + j;
         const bool has = kb < p.g_k_blocks;
         const int n_kb = min(4, p.g_k_blocks - 4 * (int)blockIdx.x);
-        const uint32_t tx = (uint32_t)n_kb * 8u * (UNIT * 16) + 2 * b_tile;
+        const uint32_t tx = (uint32_t)n_kb * 8u * (UNIT * 16) + NB * b_tile;
         const uint32_t a_dst = (uint32_t)part * A_PART + (uint32_t)(j * 4 + kc) * (UNIT * 16);
         const size_t a_off = (size_t)kb * tile_bytes(TR_A) + (size_t)part * part_bytes(TR_A) + (size_t)kc * (TR_A * 16);
         const uint8_t *b_src = p.B + ((size_t)blockIdx.y * p.b_k_blocks) * b_tile;
@@ -104,20 +112,20 @@ __global__ void __launch_bounds__(192) umma_dw_kernel(DwParams p, const __grid_c
             if (TMA) {
                 // k-blocks past the end of this row tile's K range (ck not a multiple of 128) come from the next row
                 // tile or are zero-filled: they only feed dW^T rows >= ck, which the epilogue drops
-                if (lane == 0) mbar_arrive_expect_tx(full_bar(s), A_STAGE + 2 * b_tile);
+                if (lane == 0) mbar_arrive_expect_tx(full_bar(s), A_STAGE + NB * b_tile);
                 __syncwarp();
                 if (lane < 2)
-                    tma_load_4d(st + lane * A_PART, &g_map, full_bar(s), (u & 1) * (UNIT * 4), 0, lane,
-                                (u >> 1) * p.g_k_blocks + 4 * (int)blockIdx.x);
+                    tma_load_4d(st + lane * A_PART, &g_map, full_bar(s), (u % UPT) * (UNIT * 4), 0, lane,
+                                (u / UPT) * p.g_k_blocks + 4 * (int)blockIdx.x);
             } else {
                 if (lane == 0) mbar_arrive_expect_tx(full_bar(s), tx);
                 __syncwarp();
                 if (has)
-                    bulk_g2s(st + a_dst, p.G + (size_t)(u >> 1) * p.g_k_blocks * tile_bytes(TR_A) + a_off + (size_t)(u & 1) * (UNIT * 16),
+                    bulk_g2s(st + a_dst, p.G + (size_t)(u / UPT) * p.g_k_blocks * tile_bytes(TR_A) + a_off + (size_t)(u % UPT) * (UNIT * 16),
                              UNIT * 16, full_bar(s));
             }
-            if (lane < 2)
-                bulk_g2s(st + A_STAGE + lane * b_tile, b_src + (size_t)(2 * u + lane) * b_tile, b_tile, full_bar(s));
+            if (lane < NB)
+                bulk_g2s(st + A_STAGE + lane * b_tile, b_src + (size_t)(NB * u + lane) * b_tile, b_tile, full_bar(s));
         }
     } else {
         // the MMA warp runs converged and issues through elect.sync (epn_umma.cuh, "warp-converged issue")
@@ -175,7 +183,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_tile_map(CUtensorMap *map, const void *tiles, unsigned long long n_kblocks_total) {
+int encode_tile_map(CUtensorMap *map, const void *tiles, unsigned long long n_kblocks_total, int unit) {
     static EncodeTiledFn fn = [] {
         void *p = nullptr;
         cudaDriverEntryPointQueryResult q;
@@ -186,7 +194,7 @@ int encode_tile_map(CUtensorMap *map, const void *tiles, unsigned long long n_kb
     if (fn == nullptr) return 1;
     const cuuint64_t dims[4] = {512, 4, 2, n_kblocks_total};     // 32-bit words
     const cuuint64_t strides[3] = {2048, 8192, 16384};            // bytes, dims 1..3
-    const cuuint32_t box[4] = {(cuuint32_t)UNIT * 4, 4, 1, 4};    // 64 rows x 16 B = 256 words
+    const cuuint32_t box[4] = {(cuuint32_t)unit * 4, 4, 1, 4};    // `unit` rows x 16 B (64 rows = 256 words)
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(tiles), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -199,21 +207,29 @@ int encode_tile_map(CUtensorMap *map, const void *tiles, unsigned long long n_kb
 // G_tiles: forward operand tiles of one slab (n rows, n % 128 == 0, K = ck); B_tiles: dout tiles (rows = c_out, K = n)
 int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, long long n, int trb, float *dW,
                    int kperm, cudaStream_t s) {
-    if (n % 128 != 0 || n / UNIT >= (1LL << 31)) {
+    if (n % 128 != 0) {
         set_error("umma_dw: n must be a multiple of 128");
         return EPN_ERR_SHAPE;
     }
-    static DynSmemOnce once, once_tma;
-    if (int rc = ensure_dyn_smem(once, umma_dw_kernel<false>, 220 * 1024, "umma_dw_kernel")) return rc;
-    if (int rc = ensure_dyn_smem(once_tma, umma_dw_kernel<true>, 220 * 1024, "umma_dw_kernel")) return rc;
+    static const int unit32_from = getenv("EPN_DW_UNIT32_FROM") ? atoi(getenv("EPN_DW_UNIT32_FROM")) : 129;   // tuning knob: dout-tile rows from which UNIT = 32
+    const int unit = trb >= unit32_from ? 32 : 64;
+    if (n / unit >= (1LL << 31)) {
+        set_error("umma_dw: n too large");
+        return EPN_ERR_SHAPE;
+    }
+    static DynSmemOnce once, once_tma, once32, once32_tma;
+    if (int rc = ensure_dyn_smem(once, umma_dw_kernel<false, 64>, 220 * 1024, "umma_dw_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once_tma, umma_dw_kernel<true, 64>, 220 * 1024, "umma_dw_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once32, umma_dw_kernel<false, 32>, 220 * 1024, "umma_dw_kernel")) return rc;
+    if (int rc = ensure_dyn_smem(once32_tma, umma_dw_kernel<true, 32>, 220 * 1024, "umma_dw_kernel")) return rc;
     DwParams p;
     p.G = static_cast<const uint8_t *>(G_tiles);
     p.B = static_cast<const uint8_t *>(B_tiles);
     p.g_k_blocks = (ck + KB - 1) / KB;
     p.b_k_blocks = (int)(n / KB);
-    p.units = (int)(n / UNIT);
+    p.units = (int)(n / unit);
     p.trb = trb;
-    const size_t stage = A_STAGE + 2 * tile_bytes(trb);
+    const size_t stage = (unit == 64 ? DwCfg<64>::A_STAGE : DwCfg<32>::A_STAGE) + (size_t)(unit / 32) * tile_bytes(trb);
     int stages;
     if (2 * stage <= 110 * 1024) {
         stages = (int)((110 * 1024) / stage);  // two CTAs per SM: one's RED epilogue overlaps the other's main loop
@@ -243,10 +259,13 @@ int launch_umma_dw(const void *G_tiles, const void *B_tiles, int ck, int c_out, 
     static const int use_tma = (getenv("EPN_DW_TMA") && atoi(getenv("EPN_DW_TMA")) == 0) ? 0 : 1;
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    if (use_tma && encode_tile_map(&map, G_tiles, (unsigned long long)(n / TR_A) * p.g_k_blocks) == 0) {
-        umma_dw_kernel<true><<<grid, 192, smem, s>>>(p, map);
+    const bool tma = use_tma && encode_tile_map(&map, G_tiles, (unsigned long long)(n / TR_A) * p.g_k_blocks, unit) == 0;
+    if (unit == 64) {
+        if (tma) umma_dw_kernel<true, 64><<<grid, 192, smem, s>>>(p, map);
+        else umma_dw_kernel<false, 64><<<grid, 192, smem, s>>>(p, map);
     } else {
-        umma_dw_kernel<false><<<grid, 192, smem, s>>>(p, map);
+        if (tma) umma_dw_kernel<true, 32><<<grid, 192, smem, s>>>(p, map);
+        else umma_dw_kernel<false, 32><<<grid, 192, smem, s>>>(p, map);
     }
     return check_launch("umma_dw_kernel");
 }
