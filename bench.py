@@ -39,7 +39,7 @@ METRIC = "point-clouds/sec, ModelNet40 1024-pt 60-anchor SPConv fwd+bwd"
 N_POINTS, N_ANCHORS, KS, KN = 1024, 60, 24, 12
 CLASSES = ["index_ops", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group", "channel_gemm", "split_convert",
            "norm_act", "inter_fused_fwd"]
-DTYPE = "f32 (bf16x3 tensor-core operands, fp32 accumulate; SIMT stages fp32)"
+DTYPE = "f32 (tensor-core operands split hi/lo: bf16x3 in training, fp16x3 in the no_grad forward; fp32 accumulate; SIMT stages fp32)"
 
 
 # ---------------------------------------------------------------------------------------------- synthetic data
@@ -165,7 +165,7 @@ class Workload:
         totals of the forward."""
         A = N_ANCHORS
         gemm_f = group_f = scatter_f = 0.0
-        group_b = scatter_b = intra_b = 0.0
+        group_b = scatter_b = intra_b = norm_b = split_b = 0.0
         fused_b = fused_f = 0.0
         ifu_b = ifu_f = 0.0
         for c_in, c_out, p_in, p, k in self.layer_table():
@@ -184,6 +184,11 @@ class Workload:
                 group_b += feats_in + 12.0 * p_in + 4.0 * p * k + grouped
             scatter_b += (feats_in + 12.0 * p_in + 4.0 * p * k + grouped) if has_dx else 0.0
             intra_b += 4.0 * c_out * p * A + 4.0 * c_out * KN * p * A                   # training forward gather into kept tiles
+            # pass-level bytes of the HBM-bound helper kernels (what each pass must read + write; under the fused-layer
+            # accounting of SURVEY 8(d) all of this is overhead with zero algorithmic bytes)
+            t_out, t_skip = 4.0 * c_out * p * A, 4.0 * c_in * p * A
+            norm_b += 25.0 * t_out    # 3 norms per block: fwd stats + apply (+ residual) = 10 passes, bwd reduce + apply = 15
+            split_b += 2.0 * (6.0 * t_out + 2.0 * t_skip)   # dout of 3 convs in 2 orientations; skip-conv input fwd + dW
             fused_b += feats_in + 12.0 * p_in + 4.0 * c_out * p * A + 4.0 * p * k + 8.0 * c_out * p * A
             fused_f += spatial + inter_gemm + intra_gemm
             if has_dx:   # the layers the fused inter-conv kernel runs (layer 0 has its own single-channel kernel)
@@ -191,7 +196,8 @@ class Workload:
                 ifu_f += spatial + inter_gemm
         return {"channel_gemm": (gemm_f * clouds, None), "inter_group_fwd": (group_f * clouds, group_b * clouds),
                 "inter_group_bwd_scatter": (scatter_f * clouds, scatter_b * clouds), "intra_group": (None, intra_b * clouds),
-                "fused_forward": (fused_f * clouds, fused_b * clouds), "inter_fused_fwd": (ifu_f * clouds, ifu_b * clouds)}
+                "fused_forward": (fused_f * clouds, fused_b * clouds), "inter_fused_fwd": (ifu_f * clouds, ifu_b * clouds),
+                "norm_act": (None, norm_b * clouds), "split_convert": (None, split_b * clouds)}
 
 
 class ClockSampler:
@@ -329,6 +335,8 @@ class Runner:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+                os.environ["NCCL_DEBUG"] = "WARN"   # no "NCCL version ..." banner on stdout next to the JSON line
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -533,7 +541,9 @@ def main():
         else:
             ach = nbytes / t / 1e9
             r = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                 "note": "grouping-stage bytes of SURVEY.md 8(d)"}
+                 "note": "grouping-stage bytes of SURVEY.md 8(d)" if cls not in ("norm_act", "split_convert") else
+                         "pass-level bytes (what each pass must read + write): how close the passes run to HBM speed; under the "
+                         "fused-layer accounting of SURVEY 8(d) these passes carry no algorithmic bytes at all"}
             alg = nbytes
         traffic = None
         try:
@@ -547,7 +557,8 @@ def main():
                   "per_launch": {"algorithmic": alg / per_launch, "avg_ms": kernel_ms[cls] / per_launch}})
         return r
 
-    rooflines = {c: roof_of(c) for c in ("channel_gemm", "inter_fused_fwd", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group")}
+    rooflines = {c: roof_of(c) for c in ("channel_gemm", "inter_fused_fwd", "inter_group_fwd", "inter_group_bwd_scatter", "intra_group",
+                                         "norm_act", "split_convert")}
     rooflines = {c: r for c, r in rooflines.items() if r is not None}
     dom = max(rooflines, key=lambda c: rooflines[c]["ms_per_step"])
 

@@ -158,3 +158,40 @@ def test_flat_grad_all_reduce_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0].decode() for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, o
+
+
+def test_checkpoint_io_in_the_reference_format(tmp_path):
+    """f4: a reference checkpoint (plain CPU state_dict, optionally with DataParallel's `module.` prefix or a
+    {"model": ...} wrapper, vgtk/vgtk/app/trainer.py:177-223) loads key for key into the mirrored model, a mismatch is
+    reported, and save_checkpoint writes what the reference's _save_network would."""
+    import torch
+    from conftest import load_golden
+    from epn_pointcloud_b200.blocks import SO3ConvBackbone
+    from epn_pointcloud_b200.checkpoint import load_checkpoint, save_checkpoint
+    g = load_golden("backbone_small")
+    ref_sd = g.state_dict()                       # produced by the reference's own modules (oracle/make_golden.py)
+    path = str(tmp_path / "ref_net_10.pth")
+    torch.save(ref_sd, path)
+    model = SO3ConvBackbone(g["params"], 60)
+    assert load_checkpoint(model, path) == ([], [])
+    for k, v in ref_sd.items():
+        assert torch.equal(model.state_dict()[k].reshape(v.shape), v), k
+    # DataParallel-style keys inside a {"model": ...} wrapper
+    model2 = SO3ConvBackbone(g["params"], 60)
+    load_checkpoint(model2, {"model": {"module." + k: v for k, v in ref_sd.items()}, "epoch": 3})
+    assert all(torch.equal(model2.state_dict()[k].reshape(v.shape), v) for k, v in ref_sd.items())
+    # a checkpoint of another architecture is refused with the offending keys named
+    bad = dict(ref_sd)
+    k0 = next(k for k in bad if k.endswith("basic_conv.W"))
+    bad[k0] = bad[k0][:, :-1]
+    bad["extra.weight"] = torch.zeros(1)
+    try:
+        load_checkpoint(model2, bad)
+        assert False, "mismatch not reported"
+    except RuntimeError as e:
+        assert "extra.weight" in str(e) and k0 in str(e)
+    # round trip: what save_checkpoint writes is a plain CPU state_dict with exactly the reference's keys
+    out = save_checkpoint(torch.nn.DataParallel(model) if False else model, str(tmp_path / "out.pth"))
+    back = torch.load(out, weights_only=True)
+    assert list(back.keys()) == list(ref_sd.keys()) and all(not v.is_cuda for v in back.values())
+    assert all(torch.equal(back[k].reshape(ref_sd[k].shape), ref_sd[k]) for k in ref_sd)
