@@ -62,6 +62,9 @@ struct FusedParams {
     long long keep_cols_per_z;
     size_t keep_slab_bytes;
     int c, c_out, p_in, p, nn, p_off, trb, nst, sps;   // sps: 16-k steps per weight-ring stage (1, 2 or 3)
+    int na;                  // anchors of the tensors in global memory (<= 60, multiple of 4); the kernel's lane / shared
+                             // memory geometry is always the 60-anchor one, lanes >= na are dead (anchor subsets:
+                             // so3conv/functional.py:281-289, the sweep's "first 12 anchors")
     uint32_t tmem_cols;      // columns of ONE accumulator; the kernel allocates two (see acc_cross)
     float out_scale;         // accumulator -> out factor (1 / F16_W_SCALE for fp16 operands, else 1)
 };
@@ -249,7 +252,7 @@ inter_fused_kernel(FusedParams P) {
         const int aa = ptid % FU_LANES, grp = ptid / FU_LANES;
         const int k0 = grp * KG;
         constexpr bool a_ok = true;
-        const float *F = P.feats + (size_t)z * P.c * P.p_in * NA;
+        const float *F = P.feats + (size_t)z * P.c * P.p_in * P.na;
         const NeighbourList<C::CAP> &L = s_L[HALVES ? 0 : pt];
         float *Fp = Fs + (size_t)pt * 2 * CCH * NN * NA;
         const int total_nn = L.total;
@@ -264,7 +267,7 @@ inter_fused_kernel(FusedParams P) {
         uint8_t *keep_base = nullptr;
         if (P.keep != nullptr) {
             const int zs = z / P.keep_slab_clouds, zl = z - zs * P.keep_slab_clouds;
-            const long long row = (long long)zl * P.keep_cols_per_z + (long long)pl * NA + aa;
+            const long long row = (long long)zl * P.keep_cols_per_z + (long long)pl * P.na + aa;
             keep_base = P.keep + (size_t)zs * P.keep_slab_bytes + ((size_t)(row >> 7) * P.keep_k_blocks) * tile_bytes(TR_A) +
                         (size_t)(row & 127) * 16;
         }
@@ -307,7 +310,7 @@ inter_fused_kernel(FusedParams P) {
             {
                 float R[9];
 #pragma unroll
-                for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + aa * 9 + i);
+                for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + (aa < P.na ? aa : 0) * 9 + i);   // dead lanes: any valid anchor
                 const float inv_sigma = 1.0f / P.g.sigma;
                 const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
 #pragma unroll
@@ -340,15 +343,15 @@ inter_fused_kernel(FusedParams P) {
                     for (int it = 0; it < (PIECES + PT_THR - 1) / PT_THR; ++it) {
                         const int t = ptid + it * PT_THR;
                         const int piece = t % (NA / 4), slot = t / (NA / 4), cl = slot / NN, n = slot % NN;
-                        if (t < PIECES && n < nn) {
-                            const float *src = F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA + piece * 4;
+                        if (t < PIECES && n < nn && piece * 4 < P.na) {
+                            const float *src = F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * P.na + piece * 4;
                             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
                                          ::"r"(fs_u32 + (uint32_t)((((buf * CCH + cl) * NN + n) * NA + piece * 4) * 4)), "l"(src) : "memory");
                         }
                     }
                     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
                 } else {
-                    constexpr uint32_t ROW_BYTES = NA * 4;
+                    const uint32_t ROW_BYTES = (uint32_t)P.na * 4u;
                     constexpr int SLOTS = CCH * NN;                       // 64 / 128 rows
                     constexpr int SPREAD = GATHER == 1 ? PT_THR / SLOTS : 1;   // 3: every third thread owns a row
                     if (ptid == 0) mbar_arrive_expect_tx(bar, (uint32_t)(CCH * nn) * ROW_BYTES);
@@ -357,7 +360,7 @@ inter_fused_kernel(FusedParams P) {
                         const int cl = t / NN, n = t % NN;
                         if (n < nn)
                             bulk_g2s(fs_u32 + (uint32_t)(((buf * CCH + cl) * NN + n) * NA) * 4u,
-                                     F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * NA, ROW_BYTES, bar);
+                                     F + ((size_t)(chunk * CCH + cl) * P.p_in + L.idx[n_first + n]) * P.na, ROW_BYTES, bar);
                     }
                 }
                 ++ci;
@@ -478,7 +481,7 @@ inter_fused_kernel(FusedParams P) {
             // rows r and r + 64 are the two partial results of (point, anchor r): quarters 2,3 hand theirs over through
             // shared memory (the A tiles are free: every MMA has completed), quarters 0,1 add and store
             float *stage = reinterpret_cast<float *>(a_tiles) + (size_t)(warp >> 2) * (32 * 64);   // [32 channels][64 rows]
-            float *orow = P.out + (size_t)z * P.out_sz + (size_t)blockIdx.x * NA + ra;
+            float *orow = P.out + (size_t)z * P.out_sz + (size_t)blockIdx.x * P.na + ra;
             for (int cg0 = 0; cg0 * 32 < P.c_out; cg0 += NWARPS / 4) {
                 const int cg = cg0 + (warp >> 2);
                 const bool active = cg * 32 < P.c_out;   // uniform over the four warps that share a staging area
@@ -489,7 +492,7 @@ inter_fused_kernel(FusedParams P) {
                     for (int jj = 0; jj < 32; ++jj) stage[jj * 64 + ra] = v[jj];
                 }
                 __syncthreads();
-                if (active && rpt == 0 && ra < NA) {
+                if (active && rpt == 0 && ra < P.na) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
                         const int o = cg * 32 + jj;
@@ -499,11 +502,11 @@ inter_fused_kernel(FusedParams P) {
                 __syncthreads();
             }
         } else if (rpt < PTS) {                         // warp-uniform (PTS == 1: quarters 2,3 hold dead rows)
-            float *orow = P.out + (size_t)z * P.out_sz + (size_t)(blockIdx.x * PTS + rpt) * NA + ra;
+            float *orow = P.out + (size_t)z * P.out_sz + (size_t)(blockIdx.x * PTS + rpt) * P.na + ra;
             for (int cg = warp >> 2; cg * 32 < P.c_out; cg += NWARPS / 4) {
                 float v[32];
                 tmem_ld_sum2(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32), P.tmem_cols, v);
-                if (ra < NA) {
+                if (ra < P.na) {
 #pragma unroll
                     for (int jj = 0; jj < 32; ++jj) {
                         const int o = cg * 32 + jj;
@@ -559,7 +562,8 @@ static bool fused_halves_enabled() {
 
 // K' mode the fused kernel uses for this shape (0 = shape not covered).  keep = the caller wants the operand tiles.
 int inter_fused_mode(int c, int c_out, int p_cnt, int nn, int na, int ks, bool keep) {
-    if (ks != FU_KS || na != FU_NA || c_out > 256 || c < 4) return 0;
+    if (ks != FU_KS || na > FU_NA || na < 4 || na % 4 != 0 || c_out > 256 || c < 4) return 0;
+    if (keep && na != FU_NA) return 0;   // kept tiles (128-row tiles of 60-anchor rows): the 60-anchor group only
     if (nn <= 16 && c % 4 == 0 && p_cnt % 2 == 0) return 1;
     // inference (no kept tiles), longer rows: the "halves" variant of the kernel, which uses MODE 1's K' order
     // (measured: 3.10 vs 3.44 ms on the 64-channel K = 32 layer of the cls network, no gain from 128 channels on --
@@ -590,7 +594,7 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
     P.keep_cols_per_z = keep_cols_per_z;
     P.keep_slab_clouds = keep_slab_clouds > 0 ? keep_slab_clouds : 1;
     P.keep_slab_bytes = keep_slab_bytes;
-    P.c = c; P.c_out = c_out; P.p_in = p_in; P.p = p; P.nn = nn; P.p_off = p_off;
+    P.c = c; P.c_out = c_out; P.p_in = p_in; P.p = p; P.nn = nn; P.p_off = p_off; P.na = na;
     P.trb = umma_trb_for(c_out);
     uint32_t cols = 32;
     while ((int)cols < P.trb) cols *= 2;

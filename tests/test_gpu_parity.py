@@ -725,6 +725,9 @@ def test_other_config_shapes_vs_oracle_port(E, c_in, c_out, p_in, stride, nn_, r
                                              lazy_sample=(c_in != 1))
     assert torch.equal(idx.cpu(), ridx) and (sidx is None or torch.equal(sidx.cpu(), rsidx))
     assert rel_err(y.feats, ry) < FEAT_TOL
+    with torch.no_grad():   # the inference route (fused kernel; anchor subsets run it with dead anchor lanes)
+        y_inf = conv(E.SphericalPointCloud(xyz.to(DEV), feats.to(DEV), None))[3].feats
+    assert rel_err(y_inf, ry) < FEAT_TOL
     r = torch.randn(ry.shape, generator=torch.Generator().manual_seed(8))
     (ry * r).sum().backward()
     (y.feats * r.to(DEV)).sum().backward()

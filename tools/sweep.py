@@ -6,8 +6,8 @@ batch sized so that in+out bytes >= 512 MB (> 126 MB L2).  Prints one JSON line 
 the achieved fraction of the HBM and tensor rooflines of the FUSED layer accounting:
     bytes = 4*C*N*A (feats in) + 12*N (xyz) + 4*C*N*A (out) + 4*N*K (idx)
     flops = 2*C*N*A*KS*K + 2*C*C*KS*N*A + 11*N*A*KS*K
-A=12 ("first 12 anchors") and K=64 are not reference configurations; they run through the generic
-grouping kernels (the specialised ones cover 60 anchors and K <= 32).
+A=12 ("first 12 anchors") is not a reference configuration; every shape runs the fused kernel (rows of up to 128
+slots; anchor subsets use the 60-anchor lane geometry with the other lanes dead, i.e. at 1/5 of the lane efficiency).
 
     python tools/sweep.py [--quick] > profiles/sweep.jsonl
 """
@@ -73,7 +73,7 @@ def main():
                           "clouds_per_s": round(b / (ms * 1e-3), 1),
                           "fused_GBps": round(nbytes / ms / 1e6, 1), "frac_hbm": round(nbytes / ms / 1e6 / hbm, 4),
                           "TFLOPs": round(flops / ms / 1e9, 2), "frac_bf16_burst": round(flops / ms / 1e9 / tf, 4),
-                          "path": "specialised" if (a == 60 and k <= 32) else "generic"}), flush=True)
+                          "path": "fused" if a == 60 else "fused (%d of 60 anchor lanes live)" % a}), flush=True)
         del conv, feats, xyz, x
         torch.cuda.empty_cache()
 
