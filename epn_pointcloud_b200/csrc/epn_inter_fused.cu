@@ -306,26 +306,57 @@ inter_fused_kernel(FusedParams P) {
             named_bar_sync(bar_id, NPROD);      // everybody is done with the previous pass's gather buffers
             for (int t = ptid; t < 2 * CCH * NN * NA; t += PT_THR)   // never-copied rows are zero
                 if ((t / NA) % NN >= nn) Fp[t] = 0.f;
-            uint64_t w2[KG][NN / 2];
+            // Kernel weights of this thread's (anchor, KG kernel points) against the NN neighbours of the pass, in the
+            // packing the FMA loop below wants (96 registers either way):
+            //   MODE 1 / 3: wk[j][n] = (w[k0+2j][n], w[k0+2j+1][n])  -- two kernel points per register pair, the feature
+            //               enters the FFMA2 as a broadcast scalar, the accumulator pair is two finished G values;
+            //   MODE 2:     ws[i][n] scalars, broadcast against the packed features of two channels.
+            // (The first version packed two NEIGHBOURS per pair: every G value then was an (even, odd) pair that cost
+            // an extra FADD before the hi/lo split -- 6 of ~105 instructions per thread and channel.)
+            uint64_t wk[MODE != 2 ? KG / 2 : 1][MODE != 2 ? NN : 1];
+            float ws[MODE == 2 ? KG : 1][MODE == 2 ? NN : 1];
             {
                 float R[9];
 #pragma unroll
                 for (int i = 0; i < 9; ++i) R[i] = __ldg(P.g.anchors + (aa < P.na ? aa : 0) * 9 + i);   // dead lanes: any valid anchor
                 const float inv_sigma = 1.0f / P.g.sigma;
                 const uint64_t nis2 = pack_f32x2(-inv_sigma, -inv_sigma);
+                float rx[KG], ry[KG], rz[KG];
 #pragma unroll
                 for (int i = 0; i < KG; ++i) {
                     const float kx = __ldg(P.g.kernels + (k0 + i) * 3), ky = __ldg(P.g.kernels + (k0 + i) * 3 + 1),
                                 kz = __ldg(P.g.kernels + (k0 + i) * 3 + 2);
-                    const KPoint2 rk = kpoint2(R[0] * kx + R[1] * ky + R[2] * kz, R[3] * kx + R[4] * ky + R[5] * kz,
-                                               R[6] * kx + R[7] * ky + R[8] * kz);
+                    rx[i] = R[0] * kx + R[1] * ky + R[2] * kz;
+                    ry[i] = R[3] * kx + R[4] * ky + R[5] * kz;
+                    rz[i] = R[6] * kx + R[7] * ky + R[8] * kz;
+                }
+                // absent neighbours (n >= nn) have multiplicity 0 in the list: their weights come out as 0
+                const int m0 = MODE == 1 ? 0 : n_first;
+                if (MODE != 2) {
 #pragma unroll
-                    for (int n = 0; n < NN; n += 2) {
-                        // absent neighbours (n >= nn) have multiplicity 0 in the list: their weights come out as 0
-                        const int m = (MODE == 1 ? 0 : n_first) + n;
-                        w2[i][n / 2] = kernel_weight_pair(pack_f32x2(L.g[m * 3], L.g[m * 3 + 3]), pack_f32x2(L.g[m * 3 + 1], L.g[m * 3 + 4]),
-                                                          pack_f32x2(L.g[m * 3 + 2], L.g[m * 3 + 5]), rk, nis2,
-                                                          pack_f32x2(L.mult[m], L.mult[m + 1]));
+                    for (int j = 0; j < KG / 2; ++j) {
+                        const KPoint2 rk{pack_f32x2(rx[2 * j], rx[2 * j + 1]), pack_f32x2(ry[2 * j], ry[2 * j + 1]),
+                                         pack_f32x2(rz[2 * j], rz[2 * j + 1])};
+#pragma unroll
+                        for (int n = 0; n < NN; ++n) {
+                            const int m = m0 + n;
+                            const float gx = L.g[m * 3], gy = L.g[m * 3 + 1], gz = L.g[m * 3 + 2], mu = L.mult[m];
+                            wk[j][n] = kernel_weight_pair(pack_f32x2(gx, gx), pack_f32x2(gy, gy), pack_f32x2(gz, gz), rk, nis2,
+                                                          pack_f32x2(mu, mu));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KG; ++i) {
+                        const KPoint2 rk = kpoint2(rx[i], ry[i], rz[i]);
+#pragma unroll
+                        for (int n = 0; n < NN; n += 2) {
+                            const int m = m0 + n;
+                            const uint64_t w = kernel_weight_pair(pack_f32x2(L.g[m * 3], L.g[m * 3 + 3]), pack_f32x2(L.g[m * 3 + 1], L.g[m * 3 + 4]),
+                                                                  pack_f32x2(L.g[m * 3 + 2], L.g[m * 3 + 5]), rk, nis2,
+                                                                  pack_f32x2(L.mult[m], L.mult[m + 1]));
+                            unpack_f32x2(w, ws[i][n], ws[i][n + 1]);
+                        }
                     }
                 }
             }
@@ -386,27 +417,38 @@ inter_fused_kernel(FusedParams P) {
                         const int kcl0 = grp * 3, kc0 = g * 12 + grp * 3;
 #pragma unroll
                         for (int cl4 = 0; cl4 < 4; ++cl4) {
-                            uint64_t acc2[KG];
-#pragma unroll
-                            for (int i = 0; i < KG; ++i) acc2[i] = 0ull;
+                            uint64_t acc2[KG / 2];   // (G[k0+2j], G[k0+2j+1]) of this channel
                             const float *frow = fbase + cl4 * NN * NA;
+                            {   // neighbour 0 initialises (absent neighbours have zero weights and zero feature rows)
+                                const float f = frow[0];
+                                const uint64_t f2 = pack_f32x2(f, f);
 #pragma unroll
-                            for (int n4 = 0; n4 < NN; n4 += 4) {
+                                for (int j = 0; j < KG / 2; ++j) acc2[j] = mul_f32x2(wk[j][0], f2);
+                            }
+#pragma unroll
+                            for (int n = 1; n < 4; ++n) {
+                                const float f = frow[n * NA];
+                                const uint64_t f2 = pack_f32x2(f, f);
+#pragma unroll
+                                for (int j = 0; j < KG / 2; ++j) acc2[j] = fma_f32x2(wk[j][n], f2, acc2[j]);
+                            }
+#pragma unroll
+                            for (int n4 = 4; n4 < NN; n4 += 4) {
                                 if (n4 < nn) {
 #pragma unroll
-                                    for (int n = n4; n < n4 + 4; n += 2) {
-                                        const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
+                                    for (int n = n4; n < n4 + 4; ++n) {
+                                        const float f = frow[n * NA];
+                                        const uint64_t f2 = pack_f32x2(f, f);
 #pragma unroll
-                                        for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(w2[i][n / 2], f2, acc2[i]);
+                                        for (int j = 0; j < KG / 2; ++j) acc2[j] = fma_f32x2(wk[j][n], f2, acc2[j]);
                                     }
                                 }
                             }
 #pragma unroll
                             for (int ip = 0; ip < KG / 2; ++ip) {
-                                float e0, o0, e1, o1;
-                                unpack_f32x2(acc2[2 * ip], e0, o0);
-                                unpack_f32x2(acc2[2 * ip + 1], e1, o1);
-                                split2<FMT>(e0 + o0, e1 + o1, hi[cl4 * 3 + ip], lo[cl4 * 3 + ip]);
+                                float v0, v1;
+                                unpack_f32x2(acc2[ip], v0, v1);
+                                split2<FMT>(v0, v1, hi[cl4 * 3 + ip], lo[cl4 * 3 + ip]);
                             }
                             if (cl4 >= 1) {  // 6 (cl4 + 1) values so far: piece j = cl4 - 1 (values 8j .. 8j+7) is complete
                                 const int jj = cl4 - 1;
@@ -418,35 +460,33 @@ inter_fused_kernel(FusedParams P) {
                         // 8 channels (two chunks) x 3 kernel points = 24 values = K' chunks 24 g + 3 grp + {0,1,2}
 #pragma unroll
                         for (int cp = 0; cp < CCH / 2; ++cp) {  // two channels -> 6 values -> 3 packed pairs
-                            uint64_t acc2[2][KG];
+                            uint64_t acc2[KG];   // (G[c0][k0+i], G[c0+1][k0+i]): the two channels of the pair
+                            const float *fr0 = fbase + (cp * 2) * NN * NA, *fr1 = fr0 + NN * NA;
+                            {
+                                const uint64_t f2 = pack_f32x2(fr0[0], fr1[0]);
 #pragma unroll
-                            for (int q = 0; q < 2; ++q)
+                                for (int i = 0; i < KG; ++i) acc2[i] = mul_f32x2(pack_f32x2(ws[i][0], ws[i][0]), f2);
+                            }
 #pragma unroll
-                                for (int i = 0; i < KG; ++i) acc2[q][i] = 0ull;
+                            for (int n = 1; n < 4; ++n) {
+                                const uint64_t f2 = pack_f32x2(fr0[n * NA], fr1[n * NA]);
 #pragma unroll
-                            for (int n4 = 0; n4 < NN; n4 += 4) {
+                                for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(pack_f32x2(ws[i][n], ws[i][n]), f2, acc2[i]);
+                            }
+#pragma unroll
+                            for (int n4 = 4; n4 < NN; n4 += 4) {
                                 if (n4 < nn) {
 #pragma unroll
-                                    for (int n = n4; n < n4 + 4; n += 2) {
+                                    for (int n = n4; n < n4 + 4; ++n) {
+                                        const uint64_t f2 = pack_f32x2(fr0[n * NA], fr1[n * NA]);
 #pragma unroll
-                                        for (int q = 0; q < 2; ++q) {
-                                            const float *frow = fbase + (cp * 2 + q) * NN * NA;
-                                            const uint64_t f2 = pack_f32x2(frow[n * NA], frow[(n + 1) * NA]);
-#pragma unroll
-                                            for (int i = 0; i < KG; ++i) acc2[q][i] = fma_f32x2(w2[i][n / 2], f2, acc2[q][i]);
-                                        }
+                                        for (int i = 0; i < KG; ++i) acc2[i] = fma_f32x2(pack_f32x2(ws[i][n], ws[i][n]), f2, acc2[i]);
                                     }
                                 }
                             }
-                            float v[6];
+                            float v[6];   // K' order: channel-major, three kernel points each
 #pragma unroll
-                            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                                for (int i = 0; i < KG; ++i) {
-                                    float e, o;
-                                    unpack_f32x2(acc2[q][i], e, o);
-                                    v[q * KG + i] = e + o;
-                                }
+                            for (int i = 0; i < KG; ++i) unpack_f32x2(acc2[i], v[i], v[KG + i]);
 #pragma unroll
                             for (int ip = 0; ip < 3; ++ip) {
                                 split2<FMT>(v[2 * ip], v[2 * ip + 1], hi[h * 6 + cp * 3 + ip], lo[h * 6 + cp * 3 + ip]);
