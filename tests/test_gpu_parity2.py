@@ -359,3 +359,9 @@ def test_two_devices_in_one_process(E):
         outs.append((y.detach().cpu(), f.grad.cpu(), conv.basic_conv.W.grad.cpu()))
     for a, b in zip(*outs):
         assert rel_err(a, b) < 1e-5
+
+
+def test_graft_entry_smoke(E):
+    """The driver's smoke(): one small separable block on cuda:0, forward + backward, checked against the oracle."""
+    import __graft_entry__ as g
+    g.smoke()
