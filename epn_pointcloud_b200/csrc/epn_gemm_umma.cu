@@ -23,6 +23,51 @@ using namespace umma;
 // K_LANES = false: lanes run along rows (use when rows are contiguous in the source: coalesced loads and
 // contiguous 16-byte tile stores).  K_LANES = true: lanes run along 8-wide k chunks (use when k is
 // contiguous in the source: every lane reads one full 32-byte sector, a warp 1 KB).
+// Elements (row, 8 kcg .. 8 kcg + 7) of a SplitSrc matrix (zeros outside it), with the producer's normalisation applied
+// when the source carries one.  Written for instruction count -- the conversion kernels are ISSUE-bound, not HBM-bound
+// (ncu: 76 % issue-active at 39 % DRAM): the generic form did two 64-bit divisions per thread and a 64-bit multiply +
+// wrap test per element; here the z-splits are 32-bit divisions taken only when the matrix really is split (rows and K
+// are < 2^31), and the common unsplit-K case walks a pointer.
+__device__ __forceinline__ void split_load8(const SplitSrc &src, int row, int kcg, int rows, int K, float (&x)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = 0.f;
+    if (row >= rows) return;
+    const float *base = src.ptr;
+    int z = 0;
+    if (src.rows_per_z < rows) {
+        const uint32_t rpz = (uint32_t)src.rows_per_z;
+        const uint32_t zr = (uint32_t)row / rpz, rr = (uint32_t)row - zr * rpz;
+        z = (int)zr;
+        base += (long long)zr * src.stride_rz + (long long)rr * src.stride_row;
+    } else {
+        base += (long long)row * src.stride_row;
+    }
+    const int k0 = kcg * 8;
+    if (src.k_per_z >= K) {
+        const float *p = base + (long long)k0 * src.stride_k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (k0 + i < K) x[i] = __ldg(p);
+            p += src.stride_k;
+        }
+    } else {
+        const uint32_t kpz = (uint32_t)src.k_per_z;
+        uint32_t kz = (uint32_t)k0 / kpz, kj = (uint32_t)k0 - kz * kpz;
+        const float *p = base + (long long)kz * src.stride_kz + (long long)kj * src.stride_k;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (k0 + i < K) x[i] = __ldg(p);
+            p += src.stride_k;
+            if (++kj == kpz) { kj = 0; ++kz; p = base + (long long)kz * src.stride_kz; }
+        }
+    }
+    if (src.pro.stats != nullptr) {   // normalisation + leaky_relu of the producer, applied on the way in
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (k0 + i < K) x[i] = src.pro.apply(x[i], z, k0 + i);
+    }
+}
+
 template <bool K_LANES>
 __global__ void __launch_bounds__(256)
 split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int row_tiles, int k_blocks, int fmt,
@@ -33,26 +78,7 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
     for (int y = blockIdx.y; y < (K_LANES ? rows_pad : kcgs); y += gridDim.y) {
         const int row = K_LANES ? y : x_idx, kcg = K_LANES ? x_idx : y;
         float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = 0.f;
-        if (row < rows) {
-            const float *base = src.ptr;
-            if (src.rows_per_z < rows) base += (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
-            else base += (long long)row * src.stride_row;
-            long long kz = 0, kj = (long long)kcg * 8;
-            if (src.k_per_z < K) { kz = kj / src.k_per_z; kj -= kz * src.k_per_z; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (kcg * 8 + i < K) x[i] = __ldg(base + kz * src.stride_kz + kj * src.stride_k);
-                if (++kj == src.k_per_z) { kj = 0; ++kz; }
-            }
-            if (src.pro.stats != nullptr) {   // normalisation + leaky_relu of the producer, applied on the way in
-                const int z = (int)(row / src.rows_per_z);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (kcg * 8 + i < K) x[i] = src.pro.apply(x[i], z, kcg * 8 + i);
-            }
-        }
+        split_load8(src, row, kcg, rows, K, x);
         uint4 hi, lo;
         split8_fmt(x, hi, lo, fmt, scale);
         const int rt = row / tr, r = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
@@ -75,20 +101,7 @@ split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, in
         const int r = tid >> 3, kq = tid & 7;
         const int row = row0 + r, kcg = kcg0 + kq;
         float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = 0.f;
-        if (row < rows) {
-            const float *base = src.ptr;
-            if (src.rows_per_z < rows) base += (row / src.rows_per_z) * src.stride_rz + (row % src.rows_per_z) * src.stride_row;
-            else base += (long long)row * src.stride_row;
-            long long kz = 0, kj = (long long)kcg * 8;
-            if (src.k_per_z < K) { kz = kj / src.k_per_z; kj -= kz * src.k_per_z; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (kcg * 8 + i < K) x[i] = __ldg(base + kz * src.stride_kz + kj * src.stride_k);
-                if (++kj == src.k_per_z) { kj = 0; ++kz; }
-            }
-        }
+        split_load8(src, row, kcg, rows, K, x);
         split8_fmt(x, s_hi[kq][r], s_lo[kq][r], fmt, scale);
     }
     __syncthreads();
