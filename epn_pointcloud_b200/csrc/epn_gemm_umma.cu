@@ -28,27 +28,34 @@ using namespace umma;
 // (ncu: 76 % issue-active at 39 % DRAM): the generic form did two 64-bit divisions per thread and a 64-bit multiply +
 // wrap test per element; here the z-splits are 32-bit divisions taken only when the matrix really is split (rows and K
 // are < 2^31), and the common unsplit-K case walks a pointer.
-__device__ __forceinline__ void split_load8(const SplitSrc &src, int row, int kcg, int rows, int K, float (&x)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = 0.f;
-    if (row >= rows) return;
-    const float *base = src.ptr;
-    int z = 0;
+// row part: pointer to element (row, 0) and the row's z index
+__device__ __forceinline__ const float *split_row_base(const SplitSrc &src, int row, int rows, int &z) {
+    z = 0;
     if (src.rows_per_z < rows) {
         const uint32_t rpz = (uint32_t)src.rows_per_z;
         const uint32_t zr = (uint32_t)row / rpz, rr = (uint32_t)row - zr * rpz;
         z = (int)zr;
-        base += (long long)zr * src.stride_rz + (long long)rr * src.stride_row;
-    } else {
-        base += (long long)row * src.stride_row;
+        return src.ptr + (long long)zr * src.stride_rz + (long long)rr * src.stride_row;
     }
+    return src.ptr + (long long)row * src.stride_row;
+}
+// K part: elements 8 kcg .. 8 kcg + 7 of the row at `base`
+__device__ __forceinline__ void split_load8_from(const SplitSrc &src, const float *base, int z, int kcg, int K, float (&x)[8]) {
     const int k0 = kcg * 8;
     if (src.k_per_z >= K) {
         const float *p = base + (long long)k0 * src.stride_k;
+        if (k0 + 8 <= K) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            if (k0 + i < K) x[i] = __ldg(p);
-            p += src.stride_k;
+            for (int i = 0; i < 8; ++i) {
+                x[i] = __ldg(p);
+                p += src.stride_k;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                x[i] = (k0 + i < K) ? __ldg(p) : 0.f;
+                p += src.stride_k;
+            }
         }
     } else {
         const uint32_t kpz = (uint32_t)src.k_per_z;
@@ -56,7 +63,7 @@ __device__ __forceinline__ void split_load8(const SplitSrc &src, int row, int kc
         const float *p = base + (long long)kz * src.stride_kz + (long long)kj * src.stride_k;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            if (k0 + i < K) x[i] = __ldg(p);
+            x[i] = (k0 + i < K) ? __ldg(p) : 0.f;
             p += src.stride_k;
             if (++kj == kpz) { kj = 0; ++kz; p = base + (long long)kz * src.stride_kz; }
         }
@@ -67,6 +74,16 @@ __device__ __forceinline__ void split_load8(const SplitSrc &src, int row, int kc
             if (k0 + i < K) x[i] = src.pro.apply(x[i], z, k0 + i);
     }
 }
+__device__ __forceinline__ void split_load8(const SplitSrc &src, int row, int kcg, int rows, int K, float (&x)[8]) {
+    if (row >= rows) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        return;
+    }
+    int z;
+    const float *base = split_row_base(src, row, rows, z);
+    split_load8_from(src, base, z, kcg, K, x);
+}
 
 template <bool K_LANES>
 __global__ void __launch_bounds__(256)
@@ -75,10 +92,21 @@ split_tiles_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     const int x_idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (x_idx >= (K_LANES ? kcgs : rows_pad)) return;
+    // lanes along rows: the row part of the address (a division when the matrix is z-split) is computed once per thread and
+    // the thread walks over several 8-wide k chunks (the launch gives it ~4), instead of paying it for every chunk
+    int z_row = 0;
+    const float *row_base = (!K_LANES && x_idx < rows) ? split_row_base(src, x_idx, rows, z_row) : nullptr;
     for (int y = blockIdx.y; y < (K_LANES ? rows_pad : kcgs); y += gridDim.y) {
         const int row = K_LANES ? y : x_idx, kcg = K_LANES ? x_idx : y;
         float x[8];
-        split_load8(src, row, kcg, rows, K, x);
+        if (K_LANES) {
+            split_load8(src, row, kcg, rows, K, x);
+        } else if (row_base != nullptr) {
+            split_load8_from(src, row_base, z_row, kcg, K, x);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = 0.f;
+        }
         uint4 hi, lo;
         split8_fmt(x, hi, lo, fmt, scale);
         const int rt = row / tr, r = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
@@ -96,24 +124,39 @@ __global__ void __launch_bounds__(256)
 split_tiles_kcontig_kernel(SplitSrc src, uint8_t *__restrict__ dst, int rows, int K, int tr, int k_blocks, int fmt, float scale) {
     __shared__ uint4 s_hi[8][33], s_lo[8][33];
     const int tid = threadIdx.x;
-    const int row0 = blockIdx.y * 32, kcg0 = blockIdx.x * 8;
-    {
-        const int r = tid >> 3, kq = tid & 7;
-        const int row = row0 + r, kcg = kcg0 + kq;
-        float x[8];
-        split_load8(src, row, kcg, rows, K, x);
-        split8_fmt(x, s_hi[kq][r], s_lo[kq][r], fmt, scale);
-    }
-    __syncthreads();
-    {
-        const int kq = tid >> 5, r = tid & 31;
-        const int row = row0 + r, kcg = kcg0 + kq;
-        if (kcg < k_blocks * (KB / 8) && row < (rows + tr - 1) / tr * tr) {
-            const int rt = row / tr, rr = row - rt * tr, kb = kcg / (KB / 8), kc = kcg % (KB / 8);
-            uint8_t *tile = dst + ((size_t)rt * k_blocks + kb) * tile_bytes(tr);
-            *reinterpret_cast<uint4 *>(tile + (size_t)kc * tr * 16 + (size_t)rr * 16) = s_hi[kq][r];
-            *reinterpret_cast<uint4 *>(tile + part_bytes(tr) + (size_t)kc * tr * 16 + (size_t)rr * 16) = s_lo[kq][r];
+    const int row0 = blockIdx.y * 32;
+    const int kcgs = k_blocks * (KB / 8), rows_pad = (rows + tr - 1) / tr * tr;
+    // the row part of the source address (a division when the matrix is z-split) and of the tile address is computed once;
+    // the block then walks over several 64-wide k chunks (the launch gives it ~4)
+    const int lr = tid >> 3, lkq = tid & 7;
+    int z_row = 0;
+    const float *row_base = row0 + lr < rows ? split_row_base(src, row0 + lr, rows, z_row) : nullptr;
+    const int skq = tid >> 5, sr = tid & 31;
+    const int srow = row0 + sr;
+    const int rt = srow / tr, rr = srow - rt * tr;
+    uint8_t *tile_row = dst + (size_t)rt * k_blocks * tile_bytes(tr) + (size_t)rr * 16;
+    for (int kx = blockIdx.x; kx * 8 < kcgs; kx += gridDim.x) {
+        const int kcg0 = kx * 8;
+        {
+            float x[8];
+            if (row_base != nullptr) {
+                split_load8_from(src, row_base, z_row, kcg0 + lkq, K, x);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = 0.f;
+            }
+            split8_fmt(x, s_hi[lkq][lr], s_lo[lkq][lr], fmt, scale);
         }
+        __syncthreads();
+        {
+            const int kcg = kcg0 + skq;
+            if (kcg < kcgs && srow < rows_pad) {
+                uint8_t *tile = tile_row + (size_t)(kcg >> 2) * tile_bytes(tr) + (size_t)(kcg & 3) * tr * 16;
+                *reinterpret_cast<uint4 *>(tile) = s_hi[skq][sr];
+                *reinterpret_cast<uint4 *>(tile + part_bytes(tr)) = s_lo[skq][sr];
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -127,7 +170,8 @@ int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long
     const int rows_pad = row_tiles * tr, kcgs = k_blocks * (KB / 8);
     ProfScope prof(s, KC_SPLIT);
     if (src.pro.stats == nullptr && src.stride_k == 1 && src.stride_row != 1 && (rows_pad + 31) / 32 <= 65535) {
-        dim3 grid((kcgs + 7) / 8, (rows_pad + 31) / 32);
+        const int kx = (kcgs + 7) / 8;
+        dim3 grid((kx + 3) / 4, (rows_pad + 31) / 32);   // ~4 k chunks of 64 per block
         split_tiles_kcontig_kernel<<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, k_blocks, fmt,
                                                         scale);
     } else if (src.stride_k == 1 && src.stride_row != 1) {
@@ -135,7 +179,8 @@ int launch_split_tiles(const SplitSrc &src, void *dst, long long rows, long long
         split_tiles_kernel<true><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
                                                       k_blocks, fmt, scale);
     } else {
-        dim3 grid((rows_pad + 255) / 256, kcgs < 65535 ? kcgs : 65535);
+        const int ychunks = (kcgs + 3) / 4;   // ~4 k chunks per thread: amortises the per-thread set-up (see the kernel)
+        dim3 grid((rows_pad + 255) / 256, ychunks < 65535 ? ychunks : 65535);
         split_tiles_kernel<false><<<grid, 256, 0, s>>>(src, static_cast<uint8_t *>(dst), (int)rows, (int)K, tr, row_tiles,
                                                        k_blocks, fmt, scale);
     }
