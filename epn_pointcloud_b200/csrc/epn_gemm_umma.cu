@@ -385,6 +385,10 @@ umma_gemm_kernel(UmmaGemmParams p) {
 }
 
 constexpr int IDX_STR = 244;  // row stride (floats) of the whole-tile staging of the intra data-gradient epilogue
+// warps 0-3 epilogue (TMEM readers), 4 loader, 5 MMA, 6-9 helpers of the permuted reduction of the intra conv epilogues
+// (ep_kind >= 2): with 120 of the 128 epilogue threads reducing 20 outputs each, the epilogue of a C <= 128 tile took longer
+// than its MMAs; the reduction now runs on 240 threads (one tile column each)
+constexpr int PERSISTENT_THREADS = 320;
 
 // ------------------------------------------------------------------ persistent GEMM
 // Same math and operand format as umma_gemm_kernel, scheduled differently: ONE CTA per SM walks over the output
@@ -394,7 +398,7 @@ constexpr int IDX_STR = 244;  // row stride (floats) of the whole-tile staging o
 // Per-tile fixed costs of the one-tile-per-CTA kernel (launch, TMEM allocation, barrier set-up, pipeline fill
 // and drain, store drain at exit) are paid once per SM; they dominated GEMMs with a short K loop and a large
 // output (dX = W^T dout: K = c_out, 128 KB of output per tile).
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(PERSISTENT_THREADS, 1)
 umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t stg_off) {
     extern __shared__ uint8_t smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -493,14 +497,48 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
         // ep_kind 2: whole-tile staging S[128][IDX_STR] + the inverse anchor permutations inv[k][a']
         float *S = reinterpret_cast<float *>(smem_raw + (base - smem_u32(smem_raw)) + stg_off);
         int32_t *s_inv = reinterpret_cast<int32_t *>(S + 128 * IDX_STR);
+        const bool helper = warp >= 6;                                   // reduction helpers: never touch TMEM
+        const int ridx = helper ? (int)threadIdx.x - 64 : (int)threadIdx.x;   // 0..255 over the 8 reducing warps
         if (p.ep_kind >= 2) {
-            for (int i = threadIdx.x; i < 60 * 12; i += 128) {
+            for (int i = ridx; i < 60 * 12; i += 256) {
                 const int a = i / 12, k = i - a * 12;
                 if (p.ep_kind == 2) s_inv[k * 60 + p.intra_idx[i]] = a;  // source anchor of (k, a') under the inverse
                 else s_inv[k * 60 + a] = p.intra_idx[i];                 // forward: source anchor of (k, a)
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
         }
+        // one tile column (point, anchor) per reducing thread: its 12 permuted source columns sit in registers, the 10
+        // channels of the tile stream through (12 LDS + 12 FADD per output)
+        auto reduce_tile = [&](int tm, int tn) {
+            if (ridx < 240) {
+                const int col = ridx, pt = col / 60, a2 = col - pt * 60;
+                const long long gp = (long long)tn * 4 + pt;  // point index over (z, pt) of this launch
+                if (gp * 60 < p.n_valid) {
+                    int src[12];
+#pragma unroll
+                    for (int k = 0; k < 12; ++k) src[k] = k * IDX_STR + pt * 60 + s_inv[k * 60 + a2];
+                    const long long zz = gp / p.pts_per_z, pp = gp - zz * p.pts_per_z;
+                    float *drow = p.dfeats + ((zz * p.ch_total + (long long)tm * 10) * p.pts_per_z + pp) * 60 + a2;
+                    const int nch = min(10, p.ch_total - tm * 10);
+                    for (int cl = 0; cl < nch; ++cl) {
+                        const float *sblk = S + (size_t)(cl * 12) * IDX_STR;
+                        float acc_v = 0.f;
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) acc_v += sblk[src[k]];
+                        drow[(size_t)cl * p.pts_per_z * 60] = acc_v;
+                    }
+                }
+            }
+        };
+        if (helper) {
+            if (p.ep_kind >= 2) {
+                for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // the epilogue warps have staged the tile
+                    reduce_tile(tile % m_tiles, tile / m_tiles);
+                    asm volatile("bar.sync 1, 256;" ::: "memory");   // S is free for the next tile
+                }
+            }
+        } else {
         int t = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++t) {
             const int tm = tile % m_tiles, tn = tile / m_tiles;
@@ -530,31 +568,9 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
                         if (c0 + j < 240)
                             *reinterpret_cast<float4 *>(S + (size_t)tid * IDX_STR + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                // thread <-> two fixed tile columns (tid, tid + 120): their inverse-permuted source columns sit in
-                // registers, the 10 channels of the tile stream through (12 LDS + 12 FADD per output)
-                if (tid < 120) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int col = tid + h * 120, pt = col / 60, a2 = col - pt * 60;
-                        const long long gp = (long long)tn * 4 + pt;  // point index over (z, pt) of this launch
-                        if (gp * 60 >= p.n_valid) continue;
-                        int src[12];
-#pragma unroll
-                        for (int k = 0; k < 12; ++k) src[k] = k * IDX_STR + pt * 60 + s_inv[k * 60 + a2];
-                        const long long zz = gp / p.pts_per_z, pp = gp - zz * p.pts_per_z;
-                        float *drow = p.dfeats + ((zz * p.ch_total + (long long)tm * 10) * p.pts_per_z + pp) * 60 + a2;
-                        const int nch = min(10, p.ch_total - tm * 10);
-                        for (int cl = 0; cl < nch; ++cl) {
-                            const float *sblk = S + (size_t)(cl * 12) * IDX_STR;
-                            float acc_v = 0.f;
-#pragma unroll
-                            for (int k = 0; k < 12; ++k) acc_v += sblk[src[k]];
-                            drow[(size_t)cl * p.pts_per_z * 60] = acc_v;
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // S is free for the next tile
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                reduce_tile(tm, tn);
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // S is free for the next tile
             } else if (stg_off != 0u) {
                 // column-contiguous output (dX): stage 32 rows x gw columns, one asynchronous bulk store per row
                 for (int g0 = 0; g0 < p.trb; g0 += gw) {
@@ -643,6 +659,7 @@ umma_gemm_persistent_kernel(UmmaGemmParams p, int m_tiles, int n_tiles, uint32_t
             }
         }
         if (stg_off != 0u && p.ep_kind < 2) bulk_wait_read0();
+        }   // !helper
     }
     tc_fence_before();
     __syncthreads();
@@ -732,7 +749,7 @@ int launch_umma_gemm(const void *A_tiles, const void *B_tiles, int m_rows, int n
             const size_t pipe = (((size_t)pst * stage + 16 * pst + 64) + 127) & ~(size_t)127;
             const size_t smem_p = 128 + pipe + stg_bytes;
             const int ctas = (int)(total_tiles < sm_count() ? total_tiles : sm_count());
-            umma_gemm_persistent_kernel<<<ctas, 192, smem_p, s>>>(p, (int)grid.x, (int)grid.y, stg_bytes ? (uint32_t)pipe : 0u);
+            umma_gemm_persistent_kernel<<<ctas, PERSISTENT_THREADS, smem_p, s>>>(p, (int)grid.x, (int)grid.y, stg_bytes ? (uint32_t)pipe : 0u);
             return check_launch("umma_gemm_persistent_kernel");
         }
     }
@@ -827,7 +844,7 @@ int launch_umma_intra_dx(const float *dout, long long dout_stride_z, long long d
     const long long n_tiles = n / 240, total = (long long)m_tiles * n_tiles;
     const int ctas = (int)(total < sm_count() ? total : sm_count());
     ProfScope prof(s, KC_GEMM);
-    umma_gemm_persistent_kernel<<<ctas, 192, 128 + pipe + stg_bytes, s>>>(q, m_tiles, (int)n_tiles, (uint32_t)pipe);
+    umma_gemm_persistent_kernel<<<ctas, PERSISTENT_THREADS, 128 + pipe + stg_bytes, s>>>(q, m_tiles, (int)n_tiles, (uint32_t)pipe);
     return check_launch("umma_gemm_persistent_kernel(intra dX)");
 }
 

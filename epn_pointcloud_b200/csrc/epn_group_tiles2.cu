@@ -14,6 +14,10 @@
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
+#ifndef EPN_INTRA_ROWS_BLOCKS
+#define EPN_INTRA_ROWS_BLOCKS 4   // resident blocks per SM the gather kernel is compiled for (64 registers per thread)
+#endif
+
 namespace epn {
 using namespace umma;
 
@@ -21,7 +25,7 @@ using namespace umma;
 // rows = (z,p,a) columns, K = (c,k).  Thread = one row; the 12 permuted anchor positions of the row sit in
 // registers; channels are consumed in pairs (2 x 12 = 24 k = three 8-wide chunks).
 template <int NA, int KN, int PAIRS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, EPN_INTRA_ROWS_BLOCKS)
 intra_tiles_rows_kernel(const float *__restrict__ feats, const int32_t *__restrict__ intra_idx,
                         uint8_t *__restrict__ tiles, int k_blocks, int c, int p, int p_off, int p_cnt, int n_slab,
                         int rows_pad, NormPrologue pro) {
