@@ -513,7 +513,6 @@ inter_fused_kernel(FusedParams P) {
         // ------------------------------------------------------------ epilogue: TMEM -> out[z, o, p, a], all 16 warps
         mbar_wait(smem_u32(&s_accum), 0);
         tc_fence_after();
-        constexpr int NA = FU_NA;
         const int q = warp & 3;                          // TMEM lane quarter of this warp
         const int row = q * 32 + lane;                  // = pt*64 + anchor
         const int rpt = row >> 6, ra = row & 63;
