@@ -335,8 +335,6 @@ class Runner:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-                os.environ["NCCL_DEBUG"] = "WARN"   # no "NCCL version ..." banner on stdout next to the JSON line
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
