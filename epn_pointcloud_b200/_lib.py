@@ -94,6 +94,7 @@ SIGNATURES = {
     "epn_intra_so3conv_bwd_f32": (c_i, [c_f] * 7 + [c_sz, c_f, c_sz, c_u64] + [c_i] * 6 + [c_f]),
     "epn_intra_so3conv_fwd_norm_f32": (c_i, [c_f] * 4 + [c_i, c_fl] + [c_f] * 4 + [c_sz, c_f, c_sz, c_f] + [c_i] * 6 + [c_f]),
     "epn_norm_stats_f32": (c_i, [c_f] * 3 + [c_sz] + [c_i] * 4 + [c_fl, c_f]),
+    "epn_bn_track_f32": (c_i, [c_f] * 5 + [c_i, ctypes.c_longlong, c_fl, c_fl, c_f]),
     "epn_basic_conv_workspace_bytes": (c_sz, [c_i] * 4),
     "epn_basic_conv_fwd_f32": (c_i, [c_f] * 4 + [c_sz] + [c_i] * 4 + [c_f]),
     "epn_basic_conv_bwd_f32": (c_i, [c_f] * 6 + [c_sz] + [c_i] * 4 + [c_f]),

@@ -74,6 +74,11 @@ def _bn_track(norm, stats, count, bias=None):
     if not norm.track_running_stats:
         return
     with torch.no_grad():
+        if (stats.is_cuda and norm.running_mean.dtype == torch.float32 and norm.running_mean.is_contiguous()
+                and norm.running_var.is_contiguous() and norm.num_batches_tracked.dtype == torch.int64):
+            ops.bn_track(stats, None if bias is None else bias.detach().contiguous(), norm.running_mean, norm.running_var,
+                         norm.num_batches_tracked, count, norm.momentum, norm.eps)   # one launch, graph-capturable
+            return
         norm.num_batches_tracked += 1
         mean = stats[0] if bias is None else stats[0] + bias.detach()
         var = (1.0 / (stats[1] * stats[1]) - norm.eps) * (count / max(count - 1, 1))

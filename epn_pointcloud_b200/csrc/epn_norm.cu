@@ -206,9 +206,47 @@ norm_bwd_apply_kernel(const float *__restrict__ dy, const float *__restrict__ x,
     for (int i = n4 * 4 + blockIdx.x * NT + threadIdx.x; i < n; i += gridDim.x * NT) out[i] = elem(__ldg(xr + i), __ldg(dr + i));
 }
 
+// BatchNorm's running-statistics bookkeeping (nn.BatchNorm2d.forward in training mode) from the batch (mean, rstd) of
+// the fused kernels, as ONE launch: the same arithmetic as eight elementwise torch kernels per BatchNorm layer, which at
+// small per-GPU batches (strong scaling) were a visible share of the ~600 launches of a step.  One block; thread <->
+// channel.  momentum < 0: cumulative moving average (momentum=None), factor 1 / (num_batches_tracked + 1).
+__global__ void __launch_bounds__(256)
+bn_track_kernel(const float *__restrict__ stats, const float *__restrict__ bias, float *__restrict__ running_mean,
+                float *__restrict__ running_var, long long *__restrict__ num_batches_tracked, int c, float count, float momentum,
+                float eps) {
+    const long long nbt = *num_batches_tracked + 1;
+    const float m = momentum >= 0.f ? momentum : 1.0f / (float)nbt;
+    const float unbias = count / fmaxf(count - 1.0f, 1.0f);
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+        const float mean = stats[ch] + (bias ? bias[ch] : 0.f);
+        const float rstd = stats[c + ch];
+        const float var = (1.0f / (rstd * rstd) - eps) * unbias;
+        if (momentum >= 0.f) {
+            running_mean[ch] = running_mean[ch] * (1.0f - m) + m * mean;
+            running_var[ch] = running_var[ch] * (1.0f - m) + m * var;
+        } else {
+            running_mean[ch] += (mean - running_mean[ch]) * m;
+            running_var[ch] += (var - running_var[ch]) * m;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *num_batches_tracked = nbt;
+}
+
 }  // namespace epn
 
 using namespace epn;
+
+EPN_API int epn_bn_track_f32(const float *stats, const float *bias, float *running_mean, float *running_var,
+                             long long *num_batches_tracked, int c, long long count, float momentum, float eps, void *stream) {
+    EPN_REQUIRE_PTR(stats); EPN_REQUIRE_PTR(running_mean); EPN_REQUIRE_PTR(running_var); EPN_REQUIRE_PTR(num_batches_tracked);
+    EPN_REQUIRE_POS(c);
+    EPN_REQUIRE(count > 0, EPN_ERR_SHAPE, "count must be > 0");
+    cudaStream_t s = as_stream(stream);
+    ProfScope prof(s, KC_NORM);
+    bn_track_kernel<<<1, 256, 0, s>>>(stats, bias, running_mean, running_var, num_batches_tracked, c, (float)count, momentum, eps);
+    return check_launch("bn_track_kernel");
+}
 
 EPN_API size_t epn_norm_act_workspace_bytes(int b, int c) {
     if (b <= 0 || c <= 0) return 0;

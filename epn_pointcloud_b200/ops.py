@@ -502,6 +502,19 @@ def norm_stats(x, mode, eps):
     return stats
 
 
+def bn_track(stats, bias, running_mean, running_var, num_batches_tracked, count, momentum, eps):
+    """In-place running-statistics update of a training-mode BatchNorm from the batch (mean, rstd) `stats` [2,c]
+    (epn_bn_track_f32: one launch instead of eight elementwise ones); momentum None = cumulative average."""
+    _require_cuda(stats, bias, running_mean, running_var, num_batches_tracked)
+    if num_batches_tracked.dtype != torch.int64:
+        raise RuntimeError("num_batches_tracked must be int64")
+    c = running_mean.numel()
+    with torch.cuda.device(stats.device):
+        _lib.check(_lib.lib().epn_bn_track_f32(_p(stats), _p(bias), _p(running_mean), _p(running_var), _p(num_batches_tracked), c,
+                                               int(count), -1.0 if momentum is None else float(momentum), float(eps), _stream()),
+                   "epn_bn_track_f32")
+
+
 def norm_act_bwd(dy, x, gamma, beta, stats, mode, slope, need_affine_grads=True):
     _require_cuda(dy, x, gamma, beta, stats)
     b, c = x.shape[0], x.shape[1]

@@ -234,6 +234,13 @@ int epn_norm_stats_f32(const float *x, float *stats, void *workspace, size_t wor
 int epn_norm_act_fwd_f32(const float *x, const float *gamma, const float *beta, const float *residual, float *y,
                          float *stats, void *workspace, size_t workspace_bytes, int b, int c, int n, int mode,
                          float eps, float slope, void *stream);
+/* Running-statistics bookkeeping of a training-mode BatchNorm2d (what nn.BatchNorm2d.forward does next to the
+ * normalisation) from the (mean, rstd) [2*c] of epn_norm_act_fwd_f32 / epn_norm_stats_f32 (mode 1), as one launch:
+ *   mean += bias (a per-channel constant that was left out of the kernel's input, NULL = none);
+ *   var = (1 / rstd^2 - eps) * count / max(count - 1, 1);   num_batches_tracked (int64, device) += 1;
+ *   running = running * (1 - momentum) + momentum * batch    (momentum < 0: cumulative average, factor 1 / num_batches_tracked). */
+int epn_bn_track_f32(const float *stats, const float *bias, float *running_mean, float *running_var,
+                     long long *num_batches_tracked, int c, long long count, float momentum, float eps, void *stream);
 int epn_norm_act_bwd_f32(const float *dy, const float *x, const float *gamma, const float *beta,
                          const float *stats, float *dx, float *dgamma, float *dbeta, void *workspace,
                          size_t workspace_bytes, int b, int c, int n, int mode, float slope, void *stream);

@@ -815,6 +815,29 @@ def test_fused_norm_act_with_skip_bias_and_residual(E, kind):
         assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-4
 
 
+@pytest.mark.parametrize("momentum", [0.1, None])
+def test_batchnorm_running_statistics_one_launch(E, momentum):
+    """The running-mean / running-var / num_batches_tracked bookkeeping of a training-mode BatchNorm2d as ONE library
+    launch (epn_bn_track_f32), three consecutive batches, momentum 0.1 and the cumulative average (momentum=None),
+    against nn.BatchNorm2d in float64."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from epn_pointcloud_b200 import _lib
+    from epn_pointcloud_b200.blocks import norm_act
+    b, c, p, a = 3, 6, 8, 60
+    mine, ref = nn.BatchNorm2d(c, momentum=momentum).to(DEV).train(), nn.BatchNorm2d(c, momentum=momentum).double().train()
+    gen = torch.Generator().manual_seed(5)
+    for it in range(3):
+        x0 = torch.randn(b, c, p, a, generator=gen) * (1.0 + it) + 0.5 * it
+        n0 = _lib.lib().epn_launch_count()
+        with torch.no_grad():
+            norm_act(mine, x0.to(DEV), F.leaky_relu)
+            ref(x0.double())
+        assert _lib.lib().epn_launch_count() - n0 == 4          # statistics, finalize, apply, bookkeeping
+        assert int(mine.num_batches_tracked) == it + 1
+        assert rel_err(mine.running_mean, ref.running_mean) < 1e-5 and rel_err(mine.running_var, ref.running_var) < 1e-5
+
+
 def test_fused_norm_act_batchnorm_eval_mode(E):
     """Evaluation-mode BatchNorm2d -> leaky_relu (+ skip bias, + residual) as ONE apply pass with the running
     statistics (no statistics kernels), against torch in float64; the running statistics stay untouched."""
