@@ -656,6 +656,28 @@ def reference_gpu_block(R, batch):
     ms, _ = R.timed(fwd, 3)
     out["forward_ms"] = ms / 3
     out["forward_clouds_per_s"] = batch / (ms / 3 * 1e-3)
+    # parity on the bench's own batch: this engine with the reference model's weights against the reference's output
+    # (same check as tests/test_gpu_parity2.py::test_cls_network_b32_vs_reference_modules_on_gpu; bar 1e-4)
+    try:
+        from epn_pointcloud_b200.heads import ClsSO3ConvModel, cls_model_params
+        ours = ClsSO3ConvModel(cls_model_params(N_POINTS, N_ANCHORS)).to(R.dev).train()
+        ours.load_state_dict(model.state_dict(), strict=True)
+        tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False   # the reference side in true fp32
+        try:
+            with torch.no_grad():
+                lo, fo = ours(x)
+                lr, fr = model(x)
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max())
+        out["parity"] = {"what": "no_grad forward of this engine (reference weights) vs the reference modules + kernels, same %d clouds" % batch,
+                         "head_feature_max_rel_err": rel(fo, fr), "logits_max_rel_err": rel(lo, lr), "bar": 1e-4}
+        del ours, lo, fo, lr, fr
+    except Exception as e:  # parity is reported, never allowed to lose the timing block
+        out["parity"] = {"error": repr(e)[:200]}
     torch.cuda.empty_cache()
     for b2 in (batch, 12, 8, 4):
         if b2 > batch:
