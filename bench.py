@@ -160,7 +160,7 @@ class Workload:
                 p_in = p
         return rows
 
-    def algorithmic_work(self, clouds, fused=True):
+    def algorithmic_work(self, clouds, fused=True, fused_bwd=False):
         """Per-step algorithmic flops / bytes per kernel class (formulas of SURVEY.md 8(d), fp32) + the fused-layer
         totals of the forward."""
         A = N_ANCHORS
@@ -177,6 +177,9 @@ class Workload:
             gemm_f += inter_gemm * 2 + intra_gemm * 3
             spatial = 2.0 * c_in * p * A * KS * k + 11.0 * p * A * KS * k
             scatter_f += spatial if has_dx else 0.0
+            if fused_bwd and has_dx and k <= 16 and c_out % 64 == 0 and c_out <= 256 and c_in % 4 == 0 and p % 2 == 0:
+                gemm_f -= inter_gemm      # the data-gradient GEMM of these layers runs inside the fused backward kernel
+                scatter_f += inter_gemm
             grouped = 4.0 * c_in * KS * p * A
             feats_in = 4.0 * c_in * p_in * A if has_dx else 0.0
             if not (fused and has_dx):   # grouping-only kernels: every layer without the fused kernel, else layer 0 only
@@ -513,7 +516,8 @@ def main():
     tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback"
     clouds_per_gpu = items * wl.units_per_item
-    work = wl.algorithmic_work(clouds_per_gpu, fused=kernel_ms.get("inter_fused_fwd", 0.0) > 0.0)
+    work = wl.algorithmic_work(clouds_per_gpu, fused=kernel_ms.get("inter_fused_fwd", 0.0) > 0.0,
+                               fused_bwd=bool(L.epn_get_fused_inter_bwd()))
     traffic_tab = {}
     try:  # measured DRAM bytes per class from the committed ncu pass of the same step
         traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_step.json")))

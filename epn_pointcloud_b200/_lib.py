@@ -107,6 +107,8 @@ SIGNATURES = {
     "epn_get_gemm_backend": (c_i, []),
     "epn_set_fused_inter": (None, [c_i]),
     "epn_get_fused_inter": (c_i, []),
+    "epn_set_fused_inter_bwd": (None, [c_i]),
+    "epn_get_fused_inter_bwd": (c_i, []),
     "epn_set_forward_operands": (None, [c_i]),
     "epn_get_forward_operands": (c_i, []),
 }

@@ -19,6 +19,10 @@
 #include "epn_internal.cuh"
 #include "epn_umma.cuh"
 
+#ifndef EPN_FUSED_BWD_DEFAULT
+#define EPN_FUSED_BWD_DEFAULT 1
+#endif
+
 namespace epn {
 
 static std::atomic<int> g_backend{-1};  // 0 = tcgen05, 1 = SIMT
@@ -40,6 +44,18 @@ static int fused_enabled() {  // default ON; EPN_FUSED=0 / epn_set_fused_inter(0
     if (v < 0) {
         v = (getenv("EPN_FUSED") && strcmp(getenv("EPN_FUSED"), "0") == 0) ? 0 : 1;
         g_fused.store(v);
+    }
+    return v;
+}
+
+static std::atomic<int> g_fused_bwd{-1};
+
+static int fused_bwd_enabled() {  // fused data gradient of the inter conv (epn_inter_bwd_fused.cu); EPN_FUSED_BWD=0/1
+    int v = g_fused_bwd.load();
+    if (v < 0) {
+        const char *e = getenv("EPN_FUSED_BWD");
+        v = e ? (strcmp(e, "0") != 0 ? 1 : 0) : EPN_FUSED_BWD_DEFAULT;
+        g_fused_bwd.store(v);
     }
     return v;
 }
@@ -322,6 +338,8 @@ EPN_API size_t epn_get_slab_bytes(void) { return slab_budget_bytes(); }
 EPN_API void epn_set_gemm_backend(int simt) { g_backend.store(simt ? 1 : 0); }
 EPN_API int epn_get_gemm_backend(void) { return gemm_backend(); }
 EPN_API void epn_set_fused_inter(int on) { g_fused.store(on ? 1 : 0); }
+EPN_API void epn_set_fused_inter_bwd(int on) { g_fused_bwd.store(on ? 1 : 0); }
+EPN_API int epn_get_fused_inter_bwd(void) { return fused_bwd_enabled(); }
 EPN_API void epn_set_forward_operands(int fmt) { t_fwd_fmt = fmt == umma::FMT_F16 ? umma::FMT_F16 : umma::FMT_BF16; }
 EPN_API int epn_get_forward_operands(void) { return t_fwd_fmt; }
 EPN_API int epn_get_fused_inter(void) { return fused_enabled(); }
@@ -506,9 +524,18 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     EPN_CHECK_WS(ws.total);
     const uint8_t *keep = static_cast<const uint8_t *>(grouped);
     cudaStream_t s = as_stream(stream);
+    bool fused_bwd = false;   // data gradient by the fused kernel (all clouds in one launch): no dG slab, no scatter kernel
     if (dfeats != nullptr) {
         cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)b * c_in * p_in * na, s);
-        EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));
+        if (gemm_backend() == 0 && fused_bwd_enabled() && feats != nullptr && c_in > 1 &&
+            inter_bwd_fused_ok(c_in, c_out, p, nn, na, ks)) {
+            InterGeom ga{xyz, centers, anchors, kernels, sigma};
+            const int rc = launch_inter_bwd_fused(dout, (long long)c_out * p * na, (long long)p * na, idx, ga, W, ws.tilesWT, dfeats, 0,
+                                                  p, b, c_in, c_out, p_in, p, nn, na, ks, s);
+            if (rc != 0 && rc != 1) return rc;
+            fused_bwd = rc == 0;
+        }
+        if (!fused_bwd) EPN_TRY(prep_weights(W, c_out, ck, ws, false, true, s));
     }
     if (dW != nullptr) cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)c_out * ck, s);
     for (int b0 = 0; b0 < b; b0 += sp.bc) {
@@ -521,7 +548,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
                        (long long)p * na};
             ColsView slab{ws.slab, cols, n_slab};
             const int32_t *idx_b = idx + (size_t)b0 * p * nn;
-            if (dfeats != nullptr) {
+            if (dfeats != nullptr && !fused_bwd) {
                 // dG = W^T . dout, then scatter through the transposed spatial contraction
                 EPN_TRY(gemm_dx(W, c_out, ck, d, bc, cols, slab, ws, s));
                 int sc = launch_inter_scatter(ws.slab, cols, n_slab, idx_b, g, dfeats + (size_t)b0 * c_in * p_in * na, p0, pc,

@@ -140,6 +140,14 @@ int launch_inter_fused(const float *feats, const int32_t *idx, const InterGeom &
                        long long keep_cols_per_z, int keep_slab_clouds, size_t keep_slab_bytes, int p_off, int p_cnt,
                        int bc, int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s, int fmt = 0);
 
+// epn_inter_bwd_fused.cu -- data gradient of the inter conv in one kernel (dG = dout . W^T in TMEM, transposed spatial
+// contraction + scatter straight from TMEM); dout element (z, o, pl, a) at dout + z*stride_z + o*stride_o + pl*na + a;
+// wt_scratch >= 4 * c*ks * c_out bytes; dfeats pre-zeroed.  Returns 1 if the shape is unsupported.
+bool inter_bwd_fused_ok(int c, int c_out, int p_cnt, int nn, int na, int ks);
+int launch_inter_bwd_fused(const float *dout, long long dout_stride_z, long long dout_stride_o, const int32_t *idx,
+                           const InterGeom &g, const float *W, void *wt_scratch, float *dfeats, int p_off, int p_cnt, int bc,
+                           int c, int c_out, int p_in, int p, int nn, int na, int ks, cudaStream_t s);
+
 // epn_group_direct.cu -- inter grouping with the bf16 split in registers; the operand tiles use a permuted K order
 // (24 kernel points):  mode 1 (K <= 16 neighbours, c % 4 == 0)  K'(c,k) = (c/4)*96  + (k/6)*24 + (c%4)*6 + (k%6)
 //                      mode 2 (K <= 64 neighbours, c % 8 == 0)  K'(c,k) = (c/8)*192 + (k/3)*24 + (c%8)*3 + (k%3)

@@ -542,6 +542,11 @@ def set_fused_inter(on):
     _lib.lib().epn_set_fused_inter(1 if on else 0)
 
 
+def set_fused_inter_bwd(on):
+    """True: the data gradient of InterSO3Conv (rows of <= 16 slots) runs as ONE fused kernel; False: GEMM + scatter."""
+    _lib.lib().epn_set_fused_inter_bwd(1 if on else 0)
+
+
 @contextlib.contextmanager
 def forward_operands(fmt):
     """Operand format of the forward GEMMs issued by THIS thread inside the block: 'bf16' (default: fp32's range,
