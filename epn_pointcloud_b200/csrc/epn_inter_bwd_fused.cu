@@ -45,7 +45,7 @@ struct BwdParams {
     InterGeom g;
     const uint8_t *Wt;       // W^T step tiles: [granule][16-o step][FB_STEP_BYTES]
     float *dfeats;           // [b, c, p_in, 60], pre-zeroed
-    int c, c_out, p_in, p, nn, p_off, nst, sps;
+    int c, c_out, p_in, p, nn, p_off, nst, sps, ctrl_pick;
 };
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -54,7 +54,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
+// predicated reduction: no branch, the warp stays converged for the next tcgen05.ld
+__device__ __forceinline__ void red_add_pred(float *p, float v, uint32_t ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(ok) : "memory");
+}
 
+// PIPE: 1 = TMEM reads double-buffered in groups of 4 columns + predicated reductions; 0 = groups of 8, branches
+template <int PIPE>
 __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParams P) {
     constexpr int NA = FB_NA, KS = FB_KS, NB = 4;        // NB neighbours per thread
     extern __shared__ __align__(128) uint8_t smem[];
@@ -126,6 +136,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     const int n0 = grp * NB;
     const int nn_pt = L.total < 16 ? L.total : 16;
     const bool grp_active = n0 < nn_pt;                // warp-uniform (the lane quarter fixes the point)
+    uint32_t red_mask = 0;                             // neighbour j of this thread exists (and the row is an anchor)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red_mask |= (a_ok && n0 + j < nn_pt) ? (1u << j) : 0u;
     uint64_t w2[KS][NB / 2];                            // (neighbour 2j, 2j+1) pairs
     int qoff[NB];
     if (grp_active) {
@@ -157,9 +170,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     float *DF = P.dfeats + (size_t)z * P.c * P.p_in * NA;
     const size_t cplane = (size_t)P.p_in * NA;
 
-    // ---- control state (warp 15 only; the whole warp runs it converged, one elected lane issues)
+    // ---- control state.  Every warp is a consumer and whatever the control warp spends issuing delays the granule
+    //      for all 16 (they meet at the accumulator-empty barrier), so the role goes to a warp of the LAST neighbour
+    //      group (slots 12..15: idle as a consumer whenever its point has <= 12 distinct neighbours), on the point with
+    //      fewer neighbours.  The whole warp runs the role converged, one elected lane issues.
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    const bool is_ctrl = warp_u == FB_WARPS - 1;
+    const int ctrl_warp = ((P.ctrl_pick & 1) && s_L[0].total < s_L[1].total) ? FB_WARPS - 4 : FB_WARPS - 1;
+    const bool is_ctrl = warp_u == ctrl_warp;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ngran = P.c / FB_GCH;
     const int ksteps = P.c_out / 16;
@@ -183,6 +200,11 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     // MMAs of granule gg into accumulator buffer gg & 1 (main at +0, cross terms at +FB_ACC_STRIDE)
     auto issue_granule = [&](int gg) {
         const uint32_t buf = (uint32_t)gg & 1u;
+        if (P.ctrl_pick & 2) {
+            // while the consumers drain the buffer: request every ring stage whose MMAs have completed meanwhile
+            while (!mbar_test_wait(accempty0 + 8u * buf, (((uint32_t)gg >> 1) & 1u) ^ 1u))
+                while (loaded < total_stages && loaded - consumed < (int)nst && mbar_test_wait(wempty0 + 8u * lslot, lpar)) load_w();
+        }
         mbar_wait_q(accempty0 + 8u * buf, (((uint32_t)gg >> 1) & 1u) ^ 1u);   // every consumer has drained this buffer
         tc_fence_after();
         const uint32_t d_main = tmem_u + buf * 256u, d_cross = d_main + FB_ACC_STRIDE;
@@ -225,25 +247,47 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
         const uint32_t buf = (uint32_t)g & 1u;
         mbar_wait_q(accfull0 + 8u * buf, ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
-        if (grp_active) {
-            const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u, t_cross = t_main + FB_ACC_STRIDE;
+        const uint32_t t_main = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256u, t_cross = t_main + FB_ACC_STRIDE;
 #pragma unroll 1
-            for (int cl = 0; cl < FB_GCH; ++cl) {
+        for (int cl = 0; cl < FB_GCH; ++cl) {
+            if (grp_active) {
                 uint64_t t2[NB / 2];
 #pragma unroll
                 for (int j = 0; j < NB / 2; ++j) t2[j] = 0ull;
+                if constexpr (PIPE == 1) {
+                    // 24 columns in 6 groups of 4, double-buffered: the load of group kg+1 is in flight while kg is used
+                    uint32_t m[2][4], x[2][4];
+                    tmem_ld4(t_main + (uint32_t)(cl * KS), m[0]);
+                    tmem_ld4(t_cross + (uint32_t)(cl * KS), x[0]);
+    #pragma unroll
+                    for (int kg = 0; kg < KS / 4; ++kg) {
+                        tmem_ld_wait();
+                        if (kg + 1 < KS / 4) {
+                            tmem_ld4(t_main + (uint32_t)(cl * KS + kg * 4 + 4), m[(kg + 1) & 1]);
+                            tmem_ld4(t_cross + (uint32_t)(cl * KS + kg * 4 + 4), x[(kg + 1) & 1]);
+                        }
+    #pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float dv = __uint_as_float(m[kg & 1][i]) + __uint_as_float(x[kg & 1][i]);
+                            const uint64_t d2 = pack_f32x2(dv, dv);
+    #pragma unroll
+                            for (int j = 0; j < NB / 2; ++j) t2[j] = fma_f32x2(w2[kg * 4 + i][j], d2, t2[j]);
+                        }
+                    }
+                } else {
 #pragma unroll
-                for (int kg = 0; kg < KS / 8; ++kg) {
-                    uint32_t m[8], x[8];
-                    tmem_ld8(t_main + (uint32_t)(cl * KS + kg * 8), m);
-                    tmem_ld8(t_cross + (uint32_t)(cl * KS + kg * 8), x);
-                    tmem_ld_wait();
+                    for (int kg = 0; kg < KS / 8; ++kg) {
+                        uint32_t m[8], x[8];
+                        tmem_ld8(t_main + (uint32_t)(cl * KS + kg * 8), m);
+                        tmem_ld8(t_cross + (uint32_t)(cl * KS + kg * 8), x);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float dv = __uint_as_float(m[i]) + __uint_as_float(x[i]);
-                        const uint64_t d2 = pack_f32x2(dv, dv);
+                        for (int i = 0; i < 8; ++i) {
+                            const float dv = __uint_as_float(m[i]) + __uint_as_float(x[i]);
+                            const uint64_t d2 = pack_f32x2(dv, dv);
 #pragma unroll
-                        for (int j = 0; j < NB / 2; ++j) t2[j] = fma_f32x2(w2[kg * 8 + i][j], d2, t2[j]);
+                            for (int j = 0; j < NB / 2; ++j) t2[j] = fma_f32x2(w2[kg * 8 + i][j], d2, t2[j]);
+                        }
                     }
                 }
                 float t[NB];
@@ -251,8 +295,13 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
                 for (int j = 0; j < NB / 2; ++j) unpack_f32x2(t2[j], t[2 * j], t[2 * j + 1]);
                 float *dplane = DF + (size_t)(g * FB_GCH + cl) * cplane;
 #pragma unroll
-                for (int j = 0; j < NB; ++j)
-                    if (a_ok && n0 + j < nn_pt) atomicAdd(dplane + qoff[j], t[j]);
+                for (int j = 0; j < NB; ++j) {
+                    if constexpr (PIPE == 1) {
+                        red_add_pred(dplane + qoff[j], t[j], red_mask & (1u << j));
+                    } else {
+                        if (red_mask & (1u << j)) atomicAdd(dplane + qoff[j], t[j]);
+                    }
+                }
             }
         }
         tc_fence_before();
@@ -307,19 +356,29 @@ int launch_inter_bwd_fused(const float *dout, long long dout_stride_z, long long
     P.dout = dout; P.dout_sz = dout_stride_z; P.dout_so = dout_stride_o;
     P.idx = idx; P.g = g; P.Wt = static_cast<const uint8_t *>(wt_scratch); P.dfeats = dfeats;
     P.c = c; P.c_out = c_out; P.p_in = p_in; P.p = p; P.nn = nn; P.p_off = p_off;
-    P.sps = 4;                                            // 16-o steps per ring stage (c_out / 16 is a multiple of 4): 24 KB
     const size_t a_bytes = (size_t)(c_out / 32) * FB_A_KB;
     const size_t budget = 227 * 1024 - 4 * 1024;          // static shared memory (neighbour lists, barriers) comes on top
+    // 16-o steps per ring stage (c_out / 16 is a multiple of 4): 24 KB stages
+    static const int sps_env = [] { const char *e = getenv("EPN_FB_SPS"); return e ? atoi(e) : 0; }();
+    static const int ctrl_env = [] { const char *e = getenv("EPN_FB_CTRL"); return e ? atoi(e) : 3; }();
+    P.ctrl_pick = ctrl_env;
+    P.sps = (sps_env == 1 || sps_env == 2 || sps_env == 4) ? sps_env : 4;
     const size_t stage = (size_t)FB_STEP_BYTES * P.sps;
     if (a_bytes + 2 * stage > budget) return 1;
     int nst = (int)((budget - a_bytes) / stage);
     if (nst > 8) nst = 8;
     P.nst = nst;
-    static DynSmemOnce once;
-    if (int rc = ensure_dyn_smem(once, inter_bwd_fused_kernel, (int)budget, "inter_bwd_fused_kernel")) return rc;
+    static const int pipe = [] { const char *e = getenv("EPN_FB_PIPE"); return e ? atoi(e) : 1; }();
+    static DynSmemOnce once0, once1;
     dim3 grid(p_cnt / 2, bc);
     ProfScope prof(s, KC_INTER_SCATTER);
-    inter_bwd_fused_kernel<<<grid, FB_THREADS, a_bytes + (size_t)nst * stage, s>>>(P);
+    if (pipe == 1) {
+        if (int rc = ensure_dyn_smem(once1, inter_bwd_fused_kernel<1>, (int)budget, "inter_bwd_fused_kernel")) return rc;
+        inter_bwd_fused_kernel<1><<<grid, FB_THREADS, a_bytes + (size_t)nst * stage, s>>>(P);
+    } else {
+        if (int rc = ensure_dyn_smem(once0, inter_bwd_fused_kernel<0>, (int)budget, "inter_bwd_fused_kernel")) return rc;
+        inter_bwd_fused_kernel<0><<<grid, FB_THREADS, a_bytes + (size_t)nst * stage, s>>>(P);
+    }
     return check_launch("inter_bwd_fused_kernel");
 }
 

@@ -13,7 +13,7 @@ import json
 import re
 import sys
 
-CLASS_OF = [("umma_gemm", "channel_gemm"), ("umma_dw", "channel_gemm"), ("inter_fused", "inter_fused_fwd"),
+CLASS_OF = [("umma_gemm", "channel_gemm"), ("umma_dw", "channel_gemm"), ("inter_bwd_fused", "inter_group_bwd_scatter"), ("inter_wt_steps", "split_convert"), ("inter_fused", "inter_fused_fwd"),
             ("intra_wt_tiles", "split_convert"), ("sgemm", "channel_gemm"), ("inter_group_tiles", "inter_group_fwd"), ("inter_group_direct", "inter_group_fwd"), ("inter_w_tiles", "split_convert"),
             ("inter_group_fwd", "inter_group_fwd"), ("inter_scatter", "inter_group_bwd_scatter"),
             ("inter_group_bwd", "inter_group_bwd_scatter"), ("intra_", "intra_group"), ("split_tiles", "split_convert"),
