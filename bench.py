@@ -177,7 +177,7 @@ class Workload:
             gemm_f += inter_gemm * 2 + intra_gemm * 3
             spatial = 2.0 * c_in * p * A * KS * k + 11.0 * p * A * KS * k
             scatter_f += spatial if has_dx else 0.0
-            if fused_bwd and has_dx and k <= 16 and c_out % 64 == 0 and c_out <= 256 and c_in % 4 == 0 and p % 2 == 0:
+            if fused_bwd and has_dx and k <= (16 if fused_bwd < 2 else 32) and c_out % 64 == 0 and c_out <= 256 and c_in % 4 == 0 and p % 2 == 0:
                 gemm_f -= inter_gemm      # the data-gradient GEMM of these layers runs inside the fused backward kernel
                 scatter_f += inter_gemm
             grouped = 4.0 * c_in * KS * p * A
@@ -517,7 +517,7 @@ def main():
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback"
     clouds_per_gpu = items * wl.units_per_item
     work = wl.algorithmic_work(clouds_per_gpu, fused=kernel_ms.get("inter_fused_fwd", 0.0) > 0.0,
-                               fused_bwd=bool(L.epn_get_fused_inter_bwd()))
+                               fused_bwd=int(L.epn_get_fused_inter_bwd()))
     traffic_tab = {}
     try:  # measured DRAM bytes per class from the committed ncu pass of the same step
         traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic_per_step.json")))

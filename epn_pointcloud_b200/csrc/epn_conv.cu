@@ -50,11 +50,13 @@ static int fused_enabled() {  // default ON; EPN_FUSED=0 / epn_set_fused_inter(0
 
 static std::atomic<int> g_fused_bwd{-1};
 
-static int fused_bwd_enabled() {  // fused data gradient of the inter conv (epn_inter_bwd_fused.cu); EPN_FUSED_BWD=0/1
+// fused data gradient of the inter conv (epn_inter_bwd_fused.cu); EPN_FUSED_BWD = 0 off, 1 rows of <= 16 slots, 2 also
+// rows of 17..32 slots (two CTAs per point pair: measured neutral against GEMM + scatter on the BASELINE network)
+static int fused_bwd_enabled() {
     int v = g_fused_bwd.load();
     if (v < 0) {
         const char *e = getenv("EPN_FUSED_BWD");
-        v = e ? (strcmp(e, "0") != 0 ? 1 : 0) : EPN_FUSED_BWD_DEFAULT;
+        v = e ? (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e))) : EPN_FUSED_BWD_DEFAULT;
         g_fused_bwd.store(v);
     }
     return v;
@@ -338,7 +340,7 @@ EPN_API size_t epn_get_slab_bytes(void) { return slab_budget_bytes(); }
 EPN_API void epn_set_gemm_backend(int simt) { g_backend.store(simt ? 1 : 0); }
 EPN_API int epn_get_gemm_backend(void) { return gemm_backend(); }
 EPN_API void epn_set_fused_inter(int on) { g_fused.store(on ? 1 : 0); }
-EPN_API void epn_set_fused_inter_bwd(int on) { g_fused_bwd.store(on ? 1 : 0); }
+EPN_API void epn_set_fused_inter_bwd(int on) { g_fused_bwd.store(on < 0 ? 0 : (on > 2 ? 2 : on)); }
 EPN_API int epn_get_fused_inter_bwd(void) { return fused_bwd_enabled(); }
 EPN_API void epn_set_forward_operands(int fmt) { t_fwd_fmt = fmt == umma::FMT_F16 ? umma::FMT_F16 : umma::FMT_BF16; }
 EPN_API int epn_get_forward_operands(void) { return t_fwd_fmt; }
@@ -527,7 +529,7 @@ EPN_API int epn_inter_so3conv_bwd_f32(const float *dout, const float *feats, con
     bool fused_bwd = false;   // data gradient by the fused kernel (all clouds in one launch): no dG slab, no scatter kernel
     if (dfeats != nullptr) {
         cudaMemsetAsync(dfeats, 0, sizeof(float) * (size_t)b * c_in * p_in * na, s);
-        if (gemm_backend() == 0 && fused_bwd_enabled() && feats != nullptr && c_in > 1 &&
+        if (gemm_backend() == 0 && fused_bwd_enabled() >= (nn > 16 ? 2 : 1) && feats != nullptr && c_in > 1 &&
             inter_bwd_fused_ok(c_in, c_out, p, nn, na, ks)) {
             InterGeom ga{xyz, centers, anchors, kernels, sigma};
             const int rc = launch_inter_bwd_fused(dout, (long long)c_out * p * na, (long long)p * na, idx, ga, W, ws.tilesWT, dfeats, 0,

@@ -7,7 +7,8 @@
 //    scatter_add of the gather, so3conv/functional.py:118-218)
 //
 // A CTA owns TWO consecutive output points of one cloud = 128 rows of the MMA M dimension (row = pt*64 + anchor,
-// anchors 60..63 dead), rows of <= 16 neighbour slots.  Its dout rows [128 x C_out] are split into bf16 hi/lo ONCE and
+// anchors 60..63 dead), rows of <= 16 neighbour slots (17..32 slots: two CTAs per point pair, 16 distinct neighbours
+// each).  Its dout rows [128 x C_out] are split into bf16 hi/lo ONCE and
 // stay in shared memory as the A operand for the whole kernel (128 KB at C_out = 256: affordable because this kernel
 // needs neither gather buffers nor an A ring).  W^T streams through a ring in granules of 4 channels x 24 kernel points =
 // 96 rows (B operand, N = 96, "step" layout: every 16-o step is one contiguous block), accumulating
@@ -17,9 +18,9 @@
 // same 32 rows -- which is exactly the scatter kernel's thread mapping: thread <-> (row = (point, anchor), group of four
 // neighbours), the 24 x 4 kernel weights of that pair in registers, one fp32 RED per (channel, neighbour, anchor).
 // No shared-memory staging of dG at all.
-// Warp 15 (lane quarter 3, neighbour group 3: idle as a consumer unless a point has more than 12 distinct neighbours)
-// is also the control warp: before it consumes granule g it issues the MMAs of granule g+1 (and refills the W ring), so
-// the tensor core works on the next granule while the 16 warps scatter the current one.
+// A warp of neighbour group 3 (idle as a consumer unless its point has more than 12 distinct neighbours; the one on the
+// point with fewer neighbours) is also the control warp: before it consumes granule g it issues the MMAs of granule g+1
+// (and refills the W ring), so the tensor core works on the next granule while the 16 warps scatter the current one.
 #include <stdlib.h>
 
 #include "epn_dedup.cuh"
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     const int k_blocks = P.c_out / 32;
     uint8_t *a_tiles = smem;                                        // [k_blocks] split tiles of 128 rows
     uint8_t *ring = smem + (size_t)k_blocks * FB_A_KB;              // W^T ring, nst stages of sps steps
-    __shared__ NeighbourList<16> s_L[2];
+    __shared__ NeighbourList<32> s_L[2];
     __shared__ __align__(8) uint64_t s_wfull[8], s_wempty[8], s_accfull[2], s_accempty[2];
     __shared__ uint32_t s_tmem;
 
@@ -90,8 +91,6 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
         }
         fence_barrier_init();
     }
-    if (warp == FB_WARPS - 1) tmem_alloc(smem_u32(&s_tmem), 512);
-
     // ---- distinct neighbours of the two points (one warp per point works, everybody takes part in the barriers)
     {
         const bool worker = tid < 64;
@@ -101,6 +100,12 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
                   P.g.centers + (size_t)z * 3 * P.p, P.p_in, P.p, dpi, worker ? tid - dpt * 32 : (1 << 20), worker ? 32 : 1,
                   [] { __syncthreads(); });
     }
+
+    // Rows of 17..32 slots: CTA blockIdx.z takes the distinct neighbours [16 z, 16 z + 16) of both points (the scatter
+    // is additive over neighbours; dG is recomputed by both CTAs); nothing to do past the count of both points
+    const int nbase = blockIdx.z * 16;
+    if (nbase > 0 && s_L[0].total <= nbase && s_L[1].total <= nbase) return;
+    if (warp == FB_WARPS - 1) tmem_alloc(smem_u32(&s_tmem), 512);
 
     // ---- A operand: the dout rows of the two points, split once.  task = (8-wide o chunk, row); lanes run along rows
     //      (= along anchors: coalesced 4-byte loads of 60 consecutive floats per (o, point))
@@ -132,9 +137,9 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     const int row = q * 32 + lane, pt = row >> 6, a = row & 63;
     const bool a_ok = a < NA;
     const int aa = a_ok ? a : NA - 1;
-    const NeighbourList<16> &L = s_L[pt];
-    const int n0 = grp * NB;
-    const int nn_pt = L.total < 16 ? L.total : 16;
+    const NeighbourList<32> &L = s_L[pt];
+    const int n0 = nbase + grp * NB;
+    const int nn_pt = L.total < nbase + 16 ? L.total : nbase + 16;
     const bool grp_active = n0 < nn_pt;                // warp-uniform (the lane quarter fixes the point)
     uint32_t red_mask = 0;                             // neighbour j of this thread exists (and the row is an anchor)
 #pragma unroll
@@ -175,7 +180,8 @@ __global__ void __launch_bounds__(FB_THREADS, 1) inter_bwd_fused_kernel(BwdParam
     //      group (slots 12..15: idle as a consumer whenever its point has <= 12 distinct neighbours), on the point with
     //      fewer neighbours.  The whole warp runs the role converged, one elected lane issues.
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-    const int ctrl_warp = ((P.ctrl_pick & 1) && s_L[0].total < s_L[1].total) ? FB_WARPS - 4 : FB_WARPS - 1;
+    const int left0 = min(max(s_L[0].total - nbase, 0), 16), left1 = min(max(s_L[1].total - nbase, 0), 16);
+    const int ctrl_warp = ((P.ctrl_pick & 1) && left0 < left1) ? FB_WARPS - 4 : FB_WARPS - 1;
     const bool is_ctrl = warp_u == ctrl_warp;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const int ngran = P.c / FB_GCH;
@@ -336,7 +342,7 @@ inter_wt_steps_kernel(const float *__restrict__ W, uint8_t *__restrict__ dst, in
 }  // namespace
 
 bool inter_bwd_fused_ok(int c, int c_out, int p_cnt, int nn, int na, int ks) {
-    return ks == FB_KS && na == FB_NA && nn <= 16 && c % FB_GCH == 0 && c >= FB_GCH && c_out % 64 == 0 && c_out <= 256 &&
+    return ks == FB_KS && na == FB_NA && nn <= 32 && c % FB_GCH == 0 && c >= FB_GCH && c_out % 64 == 0 && c_out <= 256 &&
            p_cnt % 2 == 0;
 }
 
@@ -370,7 +376,7 @@ int launch_inter_bwd_fused(const float *dout, long long dout_stride_z, long long
     P.nst = nst;
     static const int pipe = [] { const char *e = getenv("EPN_FB_PIPE"); return e ? atoi(e) : 1; }();
     static DynSmemOnce once0, once1;
-    dim3 grid(p_cnt / 2, bc);
+    dim3 grid(p_cnt / 2, bc, nn > 16 ? 2 : 1);
     ProfScope prof(s, KC_INTER_SCATTER);
     if (pipe == 1) {
         if (int rc = ensure_dyn_smem(once1, inter_bwd_fused_kernel<1>, (int)budget, "inter_bwd_fused_kernel")) return rc;

@@ -543,8 +543,9 @@ def set_fused_inter(on):
 
 
 def set_fused_inter_bwd(on):
-    """True: the data gradient of InterSO3Conv (rows of <= 16 slots) runs as ONE fused kernel; False: GEMM + scatter."""
-    _lib.lib().epn_set_fused_inter_bwd(1 if on else 0)
+    """1 / True: the data gradient of InterSO3Conv (rows of <= 16 slots) runs as ONE fused kernel; 2: rows of 17..32
+    slots too; 0 / False: GEMM + scatter."""
+    _lib.lib().epn_set_fused_inter_bwd(int(on))
 
 
 @contextlib.contextmanager

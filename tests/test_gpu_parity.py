@@ -548,11 +548,13 @@ def test_fused_inter_conv_matches_two_kernel_schedule(E, c_in, c_out, p_in, stri
 @pytest.mark.parametrize("c_in,c_out,p_in,stride,nn_,b", [
     (64, 64, 512, 1, 16, 2), (128, 128, 256, 1, 16, 3), (256, 256, 128, 1, 16, 2), (8, 64, 64, 1, 16, 3), (12, 128, 50, 1, 5, 2),
     (64, 128, 96, 2, 16, 2), (32, 64, 512, 1, 16, 33),
+    (64, 128, 512, 2, 32, 2), (128, 256, 256, 2, 32, 2), (256, 256, 128, 2, 32, 3), (16, 64, 200, 1, 21, 2),
 ])
 def test_fused_inter_data_gradient_matches_gemm_plus_scatter(E, c_in, c_out, p_in, stride, nn_, b):
     """Data gradient of the inter conv as ONE kernel (dG = dout . W^T in TMEM, transposed spatial contraction and the
     scatter straight from TMEM) against the data-gradient GEMM + scatter kernel pair and the fp32 SIMT engine; rows of
-    <= 16 slots incl. short rows (5 slots), several clouds per launch, an odd point pair tail is excluded by the gate."""
+    <= 16 slots incl. short rows (5 slots), rows of 17..32 slots (two CTAs per point pair, 16 distinct neighbours each;
+    radius 0.45 gives ~26 distinct neighbours at 512 points), several clouds per launch."""
     from epn_pointcloud_b200 import _lib
     L = _lib.lib()
     conv = _layer(E, c_in, c_out, stride, nn_, 0.45, 0.1)
@@ -561,7 +563,7 @@ def test_fused_inter_data_gradient_matches_gemm_plus_scatter(E, c_in, c_out, p_i
     res = {}
     try:
         for key in ("pair", "fused", "simt"):
-            E.ops.set_fused_inter_bwd(key == "fused")
+            E.ops.set_fused_inter_bwd(2 if key == "fused" else 0)   # 2: rows of 17..32 slots too (opt-in)
             E.ops.set_gemm_backend("simt" if key == "simt" else "umma")
             f = torch.randn(b, c_in, p_in, 60, device=DEV, generator=torch.Generator(DEV).manual_seed(7)).requires_grad_(True)
             conv.zero_grad()
@@ -570,7 +572,7 @@ def test_fused_inter_data_gradient_matches_gemm_plus_scatter(E, c_in, c_out, p_i
             (y.feats * r).sum().backward()
             res[key] = (f.grad.detach(), conv.basic_conv.W.grad.detach().clone())
     finally:
-        E.ops.set_fused_inter_bwd(bool(default))
+        E.ops.set_fused_inter_bwd(int(default))
         E.ops.set_gemm_backend("umma")
     for key in ("pair", "simt"):
         assert rel_err(res["fused"][0], res[key][0]) < 3e-5, key
