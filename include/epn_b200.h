@@ -261,11 +261,12 @@ int epn_get_gemm_backend(void);
  * 0 (or EPN_FUSED=0) = grouping kernel writing operand tiles followed by the GEMM kernel.  Same results (tests). */
 void epn_set_fused_inter(int on);
 int epn_get_fused_inter(void);
-/* Data gradient of InterSO3Conv (60 anchors, 24 kernel points, C_out a multiple of 64 up to 256).  1 (default;
- * EPN_FUSED_BWD=0/1/2) = rows of <= 16 neighbour slots run ONE fused kernel (dG = dout . W^T accumulated in TMEM,
+/* Data gradient of InterSO3Conv (60 anchors, 24 kernel points, C_out a multiple of 64 up to 256).  Levels
+ * (EPN_FUSED_BWD=0/1/2): 1 = rows of <= 16 neighbour slots run ONE fused kernel (dG = dout . W^T accumulated in TMEM,
  * transposed spatial contraction + scatter straight from TMEM: the gradient of the grouped tensor never reaches HBM);
- * 2 = rows of 17..32 slots too (two CTAs per point pair; neutral on the BASELINE network, hence not the default);
- * 0 = data-gradient GEMM into a slab followed by the scatter kernel.  Same results (tests). */
+ * 2 (default) = rows of 17..32 slots too (two CTAs per point pair, 16 distinct neighbours each: +6 % on the rotation
+ * network, neutral on the classification network); 0 = data-gradient GEMM into a slab followed by the scatter kernel.
+ * Same results (tests). */
 void epn_set_fused_inter_bwd(int on);
 int epn_get_fused_inter_bwd(void);
 
