@@ -14,8 +14,8 @@
  *     (`grouped` buffer + `grouped_layout` word).  Process-wide state is limited
  *     to (a) a thread-local error string, (b) a launch counter and the optional
  *     profiling record, (c) the CONFIGURATION KNOBS at the end of this header
- *     (epn_set_gemm_backend / epn_set_slab_bytes / epn_set_fused_inter and their
- *     EPN_* environment defaults): atomics read once at the start of every call,
+ *     (epn_set_gemm_backend / epn_set_slab_bytes / epn_set_fused_inter /
+ *     epn_set_fused_inter_bwd and their EPN_* environment defaults): atomics read once at the start of every call,
  *     shared by all threads and devices of the process.  Calls are re-entrant and
  *     thread-safe; changing a knob while another thread is inside a call is
  *     allowed and affects only calls that start afterwards;
