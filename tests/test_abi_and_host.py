@@ -195,3 +195,28 @@ def test_checkpoint_io_in_the_reference_format(tmp_path):
     back = torch.load(out, weights_only=True)
     assert list(back.keys()) == list(ref_sd.keys()) and all(not v.is_cuda for v in back.values())
     assert all(torch.equal(back[k].reshape(ref_sd[k].shape), ref_sd[k]) for k in ref_sd)
+
+
+def test_fused_backward_knob_levels_and_bench_accounting():
+    """The data-gradient knob is a clamped level (0 / 1 / 2) readable back without a GPU; bench.py's per-class
+    accounting moves the data-gradient GEMM flops of the layers the fused kernel covers from the GEMM class to the
+    backward-data class without creating or losing any."""
+    from epn_pointcloud_b200 import _lib
+    L = _lib.lib()
+    old = L.epn_get_fused_inter_bwd()
+    try:
+        for given, want in ((0, 0), (1, 1), (2, 2), (7, 2), (-3, 0)):
+            L.epn_set_fused_inter_bwd(given)
+            assert L.epn_get_fused_inter_bwd() == want
+    finally:
+        L.epn_set_fused_inter_bwd(old)
+    sys.path.insert(0, ROOT)
+    import bench
+    wl = bench.Workload("cls")
+    tot = []
+    for level in (0, 1, 2):
+        w = wl.algorithmic_work(32, fused=True, fused_bwd=level)
+        tot.append((w["channel_gemm"][0], w["inter_group_bwd_scatter"][0]))
+    assert tot[0][0] > tot[1][0] > tot[2][0]                      # more layers leave the GEMM class with every level
+    for g, s_ in tot[1:]:
+        assert abs((g + s_) - (tot[0][0] + tot[0][1])) < 1e-6 * (tot[0][0] + tot[0][1])
