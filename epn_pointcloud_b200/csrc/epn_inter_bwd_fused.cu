@@ -59,7 +59,7 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
 }
-// predicated reduction: no branch, the warp stays converged for the next tcgen05.ld
+// predicated reduction (ptxas still emits a short branch around the REDG: it needs the address in uniform registers)
 __device__ __forceinline__ void red_add_pred(float *p, float v, uint32_t ok) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.global.add.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(ok) : "memory");
 }
